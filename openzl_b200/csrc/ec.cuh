@@ -1,0 +1,180 @@
+// Short-Weierstrass group arithmetic (a = 0) generic over the coordinate field
+// (Fp for G1, Fp2 for G2).
+//
+// Replaces ark_ec::models::short_weierstrass_jacobian::{GroupAffine, GroupProjective}
+// (ark-ec 0.3.0) behind Pairing::{G1, G2} (/root/reference/plugins/arkworks/src/pairing.rs:14-23).
+// Bucket accumulators use extended Jacobian ("XYZZ") coordinates: x = X/ZZ, y = Y/ZZZ with
+// ZZ^3 = ZZZ^2, identity <=> ZZ == 0.  A mixed addition costs 8M + 2S instead of ark's
+// madd-2007-bl 7M + 4S, needs no final doubling of Z, and the result is the same group
+// element.  The C ABI returns ark's Jacobian (X, Y, Z) layout: (X*ZZ, Y*ZZZ, ZZ).
+#pragma once
+#include "fp.cuh"
+
+namespace ozl {
+
+template <class F>
+struct Affine {
+  F x, y;
+};
+
+template <class F>
+struct XYZZ {
+  F x, y, zz, zzz;
+
+  static OZL_DEV XYZZ identity() {
+    XYZZ r;
+    r.x = F::zero(); r.y = F::one(); r.zz = F::zero(); r.zzz = F::zero();
+    return r;
+  }
+  OZL_DEV bool is_identity() const { return zz.is_zero(); }
+
+  static OZL_DEV XYZZ from_affine(const Affine<F>& p) {
+    XYZZ r;
+    r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::one();
+    return r;
+  }
+
+  OZL_DEV XYZZ neg() const { XYZZ r = *this; r.y = y.neg(); return r; }
+
+  // 2 * (affine p), mdbl-2008-s with a = 0
+  static OZL_DEV XYZZ dbl_affine(const Affine<F>& p) {
+    XYZZ r;
+    F u = p.y.dbl();
+    F v = u.sqr();
+    F w = u * v;
+    F s = p.x * v;
+    F xx = p.x.sqr();
+    F m = xx.dbl() + xx;
+    r.x = m.sqr() - s.dbl();
+    r.y = m * (s - r.x) - w * p.y;
+    r.zz = v;
+    r.zzz = w;
+    return r;
+  }
+
+  // dbl-2008-s with a = 0
+  OZL_DEV XYZZ dbl() const {
+    if (is_identity()) return *this;
+    XYZZ r;
+    F u = y.dbl();
+    F v = u.sqr();
+    F w = u * v;
+    F s = x * v;
+    F xx = x.sqr();
+    F m = xx.dbl() + xx;
+    r.x = m.sqr() - s.dbl();
+    r.y = m * (s - r.x) - w * y;
+    r.zz = v * zz;
+    r.zzz = w * zzz;
+    return r;
+  }
+
+  // this += affine p (madd-2008-s).  p must be a finite point.
+  OZL_DEV void add_mixed(const Affine<F>& p) {
+    if (is_identity()) {
+      *this = from_affine(p);
+      return;
+    }
+    F u2 = p.x * zz;
+    F s2 = p.y * zzz;
+    F pp = u2 - x;   // P
+    F r = s2 - y;    // R
+    if (pp.is_zero()) {
+      if (r.is_zero()) {
+        *this = dbl_affine(p);
+      } else {
+        *this = identity();
+      }
+      return;
+    }
+    F p2 = pp.sqr();
+    F p3 = pp * p2;
+    F q = x * p2;
+    F x3 = r.sqr() - p3 - q.dbl();
+    y = r * (q - x3) - y * p3;
+    x = x3;
+    zz = zz * p2;
+    zzz = zzz * p3;
+  }
+
+  // this += o (add-2008-s)
+  OZL_DEV void add(const XYZZ& o) {
+    if (o.is_identity()) return;
+    if (is_identity()) {
+      *this = o;
+      return;
+    }
+    F u1 = x * o.zz;
+    F u2 = o.x * zz;
+    F s1 = y * o.zzz;
+    F s2 = o.y * zzz;
+    F pp = u2 - u1;
+    F r = s2 - s1;
+    if (pp.is_zero()) {
+      if (r.is_zero()) {
+        *this = dbl();
+      } else {
+        *this = identity();
+      }
+      return;
+    }
+    F p2 = pp.sqr();
+    F p3 = pp * p2;
+    F q = u1 * p2;
+    F x3 = r.sqr() - p3 - q.dbl();
+    y = r * (q - x3) - s1 * p3;
+    x = x3;
+    zz = zz * o.zz * p2;
+    zzz = zzz * o.zzz * p3;
+  }
+
+  // [k] * this for a small unsigned k (left-to-right double-and-add); cold path.
+  OZL_DEV XYZZ mul_u32(uint32_t k) const {
+    XYZZ acc = identity();
+    for (int bit = 31; bit >= 0; bit--) {
+      acc = acc.dbl();
+      if ((k >> bit) & 1) acc.add(*this);
+    }
+    return acc;
+  }
+
+  // ark Jacobian (X, Y, Z): x = X/Z^2, y = Y/Z^3 with Z := ZZ
+  OZL_DEV void to_jacobian(F& X, F& Y, F& Z) const {
+    if (is_identity()) {
+      X = F::zero(); Y = F::one(); Z = F::zero();  // ark GroupProjective::zero()
+      return;
+    }
+    X = x * zz;
+    Y = y * zzz;
+    Z = zz;
+  }
+
+  // affine (x, y); returns false for the identity
+  OZL_DEV bool to_affine(Affine<F>& p) const {
+    if (is_identity()) return false;
+    F zi = zzz.inverse();          // 1/Z^3
+    F zi2 = (zi * zz).sqr();       // (1/Z)^2 = (ZZ/ZZZ)^2
+    p.x = x * zi2;
+    p.y = y * zi;
+    return true;
+  }
+
+  static OZL_DEV XYZZ load(const uint32_t* p) {
+    XYZZ r;
+    r.x = F::load(p); r.y = F::load(p + F::N); r.zz = F::load(p + 2 * F::N); r.zzz = F::load(p + 3 * F::N);
+    return r;
+  }
+  OZL_DEV void store(uint32_t* p) const {
+    x.store(p); y.store(p + F::N); zz.store(p + 2 * F::N); zzz.store(p + 3 * F::N);
+  }
+};
+
+template <class F>
+OZL_DEV Affine<F> load_affine(const uint32_t* p) {
+  Affine<F> r;
+  r.x = F::load(p);
+  r.y = F::load(p + F::N);
+  return r;
+}
+
+}  // namespace ozl

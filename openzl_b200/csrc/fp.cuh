@@ -1,0 +1,298 @@
+// Prime-field arithmetic in Montgomery form, 32-bit limbs held in registers.
+//
+// Replaces ark_ff::Fp256 / Fp384 (ark-ff 0.3.0; re-exported through `pub mod ff` at
+// /root/reference/plugins/arkworks/src/lib.rs:101-103).  Same value domain as ark: every
+// element is the fully reduced Montgomery residue a*R mod p, R = 2^(32*N) = 2^(64*limbs64),
+// so the little-endian u64 limbs ark keeps in memory can be loaded unchanged as 2x u32.
+//
+// mul() is a coarsely-integrated operand-scanning Montgomery product built from two
+// interleaved accumulators ("aligned" and "offset by one limb"), so that every 32x32->64
+// partial product lands on an even/odd register pair and the whole row is one carry chain:
+// 4N+4 fma-pipe instructions per row, no carry fix-ups.  See DESIGN.md section "Field mul".
+#pragma once
+#include "ptx.cuh"
+
+namespace ozl {
+
+template <class P>
+struct Fp {
+  static constexpr int N = P::N;
+  typedef P Params;
+  uint32_t v[N];
+
+  // ---- constants ---------------------------------------------------------------------------
+  static OZL_DEV Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = 0;
+    return r;
+  }
+  static OZL_DEV Fp one() {  // R mod p
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::one()[i];
+    return r;
+  }
+  static OZL_DEV Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::r2()[i];
+    return r;
+  }
+  static OZL_DEV Fp from_limbs(const uint32_t* c) {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = c[i];
+    return r;
+  }
+
+  // ---- predicates --------------------------------------------------------------------------
+  OZL_DEV bool is_zero() const {
+    uint32_t t = v[0];
+#pragma unroll
+    for (int i = 1; i < N; i++) t |= v[i];
+    return t == 0;
+  }
+  friend OZL_DEV bool operator==(const Fp& a, const Fp& b) {
+    uint32_t t = a.v[0] ^ b.v[0];
+#pragma unroll
+    for (int i = 1; i < N; i++) t |= a.v[i] ^ b.v[i];
+    return t == 0;
+  }
+  friend OZL_DEV bool operator!=(const Fp& a, const Fp& b) { return !(a == b); }
+
+  // ---- add / sub ---------------------------------------------------------------------------
+  // r = (x >= p) ? x - p : x, for x < 2p
+  static OZL_DEV void final_sub(uint32_t* x) {
+    uint32_t t[N];
+    t[0] = ptx::sub_cc(x[0], P::mod()[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(x[i], P::mod()[i]);
+    uint32_t borrow = ptx::subc(0, 0);  // 0xffffffff iff x < p
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = borrow ? x[i] : t[i];
+  }
+
+  friend OZL_DEV Fp operator+(const Fp& a, const Fp& b) {
+    Fp r;
+    r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    r.v[N - 1] = ptx::addc(a.v[N - 1], b.v[N - 1]);  // a + b < 2p < 2^(32N): no carry out
+    final_sub(r.v);
+    return r;
+  }
+
+  friend OZL_DEV Fp operator-(const Fp& a, const Fp& b) {
+    Fp r;
+    r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    uint32_t mask = ptx::subc(0, 0);  // all ones iff a < b
+    r.v[0] = ptx::add_cc(r.v[0], P::mod()[0] & mask);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(r.v[i], P::mod()[i] & mask);
+    r.v[N - 1] = ptx::addc(r.v[N - 1], P::mod()[N - 1] & mask);
+    return r;
+  }
+
+  OZL_DEV Fp neg() const {
+    if (is_zero()) return *this;
+    Fp r;
+    r.v[0] = ptx::sub_cc(P::mod()[0], v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.v[i] = ptx::subc_cc(P::mod()[i], v[i]);
+    r.v[N - 1] = ptx::subc(P::mod()[N - 1], v[N - 1]);
+    return r;
+  }
+  // conditional negate without divergence on the flag
+  OZL_DEV Fp cneg(bool flag) const {
+    Fp n = neg();
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = flag ? n.v[i] : v[i];
+    return r;
+  }
+
+  OZL_DEV Fp dbl() const { return *this + *this; }
+
+  // ---- Montgomery product ------------------------------------------------------------------
+  // Row helpers.  X is the accumulator whose limb k sits at weight 2^(32k) ("aligned"),
+  // Y the one whose limb k sits at weight 2^(32(k+1)) ("offset").
+  static OZL_DEV void reduce_row(uint32_t* X, uint32_t* Y) {
+    const uint32_t m = ptx::mul_lo(X[0], P::INV);
+    Y[0] = ptx::mad_lo_cc(P::mod()[1], m, Y[0]);
+    Y[1] = ptx::madc_hi_cc(P::mod()[1], m, Y[1]);
+#pragma unroll
+    for (int k = 2; k < N; k += 2) {
+      Y[k] = ptx::madc_lo_cc(P::mod()[k + 1], m, Y[k]);
+      Y[k + 1] = ptx::madc_hi_cc(P::mod()[k + 1], m, Y[k + 1]);
+    }
+    X[0] = ptx::mad_lo_cc(P::mod()[0], m, X[0]);
+    X[1] = ptx::madc_hi_cc(P::mod()[0], m, X[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      X[j] = ptx::madc_lo_cc(P::mod()[j], m, X[j]);
+      X[j + 1] = ptx::madc_hi_cc(P::mod()[j], m, X[j + 1]);
+    }
+    Y[N - 1] = ptx::addc(Y[N - 1], 0);
+  }
+
+  // Divide the running value by 2^32 (X[0] == 0 on entry) and add a * bi.
+  // On return the roles are swapped: Y is aligned, X is offset.
+  static OZL_DEV void next_row(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+    Y[0] = ptx::add_cc(Y[0], X[1]);
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+      X[k] = ptx::madc_lo_cc(a[k + 1], bi, (k + 2 < N) ? X[k + 2] : 0u);
+      X[k + 1] = ptx::madc_hi_cc(a[k + 1], bi, (k + 3 < N) ? X[k + 3] : 0u);
+    }
+    Y[0] = ptx::mad_lo_cc(a[0], bi, Y[0]);
+    Y[1] = ptx::madc_hi_cc(a[0], bi, Y[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      Y[j] = ptx::madc_lo_cc(a[j], bi, Y[j]);
+      Y[j + 1] = ptx::madc_hi_cc(a[j], bi, Y[j + 1]);
+    }
+    X[N - 1] = ptx::addc(X[N - 1], 0);
+  }
+
+  friend OZL_DEV Fp operator*(const Fp& a, const Fp& b) {
+    static_assert(N % 2 == 0, "even limb count required");
+    uint32_t A[N], B[N];
+    // row 0: pure products
+    {
+      const uint32_t b0 = b.v[0];
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        A[j] = ptx::mul_lo(a.v[j], b0);
+        A[j + 1] = ptx::mul_hi(a.v[j], b0);
+        B[j] = ptx::mul_lo(a.v[j + 1], b0);
+        B[j + 1] = ptx::mul_hi(a.v[j + 1], b0);
+      }
+      reduce_row(A, B);
+    }
+#pragma unroll
+    for (int i = 1; i < N - 1; i += 2) {
+      next_row(A, B, a.v, b.v[i]);
+      reduce_row(B, A);
+      next_row(B, A, a.v, b.v[i + 1]);
+      reduce_row(A, B);
+    }
+    next_row(A, B, a.v, b.v[N - 1]);
+    reduce_row(B, A);
+    // value = A + (B >> 32), B[0] == 0
+    Fp r;
+    r.v[0] = ptx::add_cc(A[0], B[1]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) r.v[k] = ptx::addc_cc(A[k], B[k + 1]);
+    r.v[N - 1] = ptx::addc(A[N - 1], 0);
+    final_sub(r.v);
+    return r;
+  }
+
+  OZL_DEV Fp sqr() const { return *this * *this; }
+
+  // Leave / enter Montgomery form.
+  OZL_DEV Fp from_mont() const {
+    Fp o = zero();
+    o.v[0] = 1;
+    return *this * o;
+  }
+  OZL_DEV Fp to_mont() const { return *this * r2(); }
+
+  // a^(p-2) by square-and-multiply over the bits of p - 2 (cold path: affine conversion).
+  OZL_DEV Fp inverse() const {
+    uint32_t e[N];
+    e[0] = ptx::sub_cc(P::mod()[0], 2);
+#pragma unroll
+    for (int i = 1; i < N; i++) e[i] = ptx::subc_cc(P::mod()[i], 0);
+    Fp acc = one();
+    for (int bit = P::BITS - 1; bit >= 0; bit--) {
+      acc = acc.sqr();
+      if ((e[bit >> 5] >> (bit & 31)) & 1) acc = acc * *this;
+    }
+    return acc;
+  }
+
+  // memory <-> registers (16-byte vector accesses; pointers must be 16 B aligned)
+  static OZL_DEV Fp load(const uint32_t* p) {
+    Fp r;
+#if defined(__CUDACC__)
+    static_assert(N % 4 == 0, "limb count must be a multiple of 4");
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      uint4 t = *reinterpret_cast<const uint4*>(p + i);
+      r.v[i] = t.x; r.v[i + 1] = t.y; r.v[i + 2] = t.z; r.v[i + 3] = t.w;
+    }
+#else
+    for (int i = 0; i < N; i++) r.v[i] = p[i];
+#endif
+    return r;
+  }
+  OZL_DEV void store(uint32_t* p) const {
+#if defined(__CUDACC__)
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      *reinterpret_cast<uint4*>(p + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+#else
+    for (int i = 0; i < N; i++) p[i] = v[i];
+#endif
+  }
+};
+
+// Quadratic extension Fq2 = Fq[u]/(u^2 + 1) (ark QuadExtField with NONRESIDUE = -1; both
+// BLS12-381 and BN254 use it).  Memory layout c0 || c1, each a Montgomery Fq.
+template <class P>
+struct Fp2 {
+  typedef Fp<P> Base;
+  typedef P Params;
+  static constexpr int N = 2 * P::N;
+  Base c0, c1;
+
+  static OZL_DEV Fp2 zero() { Fp2 r; r.c0 = Base::zero(); r.c1 = Base::zero(); return r; }
+  static OZL_DEV Fp2 one() { Fp2 r; r.c0 = Base::one(); r.c1 = Base::zero(); return r; }
+  static OZL_DEV Fp2 from_limbs(const uint32_t* c) {
+    Fp2 r; r.c0 = Base::from_limbs(c); r.c1 = Base::from_limbs(c + P::N); return r;
+  }
+  OZL_DEV bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  friend OZL_DEV bool operator==(const Fp2& a, const Fp2& b) { return a.c0 == b.c0 && a.c1 == b.c1; }
+  friend OZL_DEV bool operator!=(const Fp2& a, const Fp2& b) { return !(a == b); }
+  friend OZL_DEV Fp2 operator+(const Fp2& a, const Fp2& b) { Fp2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
+  friend OZL_DEV Fp2 operator-(const Fp2& a, const Fp2& b) { Fp2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
+  OZL_DEV Fp2 neg() const { Fp2 r; r.c0 = c0.neg(); r.c1 = c1.neg(); return r; }
+  OZL_DEV Fp2 cneg(bool f) const { Fp2 r; r.c0 = c0.cneg(f); r.c1 = c1.cneg(f); return r; }
+  OZL_DEV Fp2 dbl() const { Fp2 r; r.c0 = c0.dbl(); r.c1 = c1.dbl(); return r; }
+  // Karatsuba: 3 base multiplications
+  friend OZL_DEV Fp2 operator*(const Fp2& a, const Fp2& b) {
+    Base t0 = a.c0 * b.c0;
+    Base t1 = a.c1 * b.c1;
+    Base t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+    Fp2 r;
+    r.c0 = t0 - t1;
+    r.c1 = t2 - t0 - t1;
+    return r;
+  }
+  // complex squaring: 2 base multiplications
+  OZL_DEV Fp2 sqr() const {
+    Base s = c0 + c1;
+    Base d = c0 - c1;
+    Base m = c0 * c1;
+    Fp2 r;
+    r.c0 = s * d;
+    r.c1 = m.dbl();
+    return r;
+  }
+  OZL_DEV Fp2 inverse() const {
+    Base n = (c0.sqr() + c1.sqr()).inverse();
+    Fp2 r;
+    r.c0 = c0 * n;
+    r.c1 = (c1 * n).neg();
+    return r;
+  }
+  static OZL_DEV Fp2 load(const uint32_t* p) { Fp2 r; r.c0 = Base::load(p); r.c1 = Base::load(p + P::N); return r; }
+  OZL_DEV void store(uint32_t* p) const { c0.store(p); c1.store(p + P::N); }
+};
+
+}  // namespace ozl

@@ -1,0 +1,100 @@
+// Carry-chain primitives for multi-limb integer arithmetic on sm_100a.
+//
+// Each wrapper is exactly one PTX instruction using the per-thread carry flag CC.CF
+// (add.cc / addc / sub.cc / subc / mad.{lo,hi}.cc / madc.{lo,hi}.cc).  ptxas turns the
+// carry flag into predicate registers and pairs mad.lo.cc + madc.hi.cc into
+// IMAD.WIDE.U32(.X) on the fma pipe, which is what bounds every kernel in this library.
+//
+// When compiled WITHOUT nvcc and with -DOZL_HOST_EMU the same wrappers are emulated with a
+// thread-local carry bit.  That build exists only so tests/ can exercise the limb-level
+// algorithms of fp.cuh / ec.cuh with g++ on a machine that has no GPU; the product library
+// never contains it.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define OZL_DEV __device__ __forceinline__
+#define OZL_HOSTDEV __host__ __device__ __forceinline__
+#else
+#ifndef OZL_HOST_EMU
+#error "ptx.cuh needs nvcc (or -DOZL_HOST_EMU for the g++ test build)"
+#endif
+#define OZL_DEV inline
+#define OZL_HOSTDEV inline
+#endif
+
+namespace ozl {
+namespace ptx {
+
+#if defined(__CUDACC__)
+
+OZL_DEV uint32_t add_cc(uint32_t a, uint32_t b) {
+  uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+OZL_DEV uint32_t addc_cc(uint32_t a, uint32_t b) {
+  uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+OZL_DEV uint32_t addc(uint32_t a, uint32_t b) {
+  uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+OZL_DEV uint32_t sub_cc(uint32_t a, uint32_t b) {
+  uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+OZL_DEV uint32_t subc_cc(uint32_t a, uint32_t b) {
+  uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+OZL_DEV uint32_t subc(uint32_t a, uint32_t b) {
+  uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+OZL_DEV uint32_t mul_lo(uint32_t a, uint32_t b) {
+  uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+OZL_DEV uint32_t mul_hi(uint32_t a, uint32_t b) {
+  uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+OZL_DEV uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+OZL_DEV uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+OZL_DEV uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+OZL_DEV uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+OZL_DEV uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+
+#else  // ---- g++ emulation (tests only) ----------------------------------------------------
+
+static thread_local uint32_t g_cf = 0;
+
+inline uint32_t add_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b; g_cf = (uint32_t)(t >> 32); return (uint32_t)t;
+}
+inline uint32_t addc_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b + g_cf; g_cf = (uint32_t)(t >> 32); return (uint32_t)t;
+}
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + g_cf; }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b; g_cf = (uint32_t)((t >> 32) & 1); return (uint32_t)t;
+}
+inline uint32_t subc_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b - g_cf; g_cf = (uint32_t)((t >> 32) & 1); return (uint32_t)t;
+}
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - g_cf; }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(a * b, c); }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(a * b, c); }
+inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc(mul_hi(a, b), c); }
+
+#endif
+
+}  // namespace ptx
+}  // namespace ozl
