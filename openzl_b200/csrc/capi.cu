@@ -1,0 +1,636 @@
+// C ABI of libozl_b200 (see include/ozl.h).  Host-side runtime: context, device workspace,
+// bases registry, window planning, kernel sequencing and stage timing.  No CPU compute path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ozl.h"
+#include "params_gen.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+using namespace ozl;
+using namespace ozl_params;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct Bases {
+  int curve = -1;
+  size_t n = 0;
+  uint32_t* d_pts = nullptr;   // n * 2 * coord_u32
+  uint8_t* d_inf = nullptr;    // optional bitset
+};
+
+struct Stage {
+  std::string name;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int launches = 0;
+};
+
+}  // namespace
+
+struct ozl_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  std::map<uint32_t, Bases> bases;
+  uint32_t next_handle = 1;
+  int forced_c = 0;
+  uint64_t launches = 0;
+  bool timing = false;
+  std::vector<Stage> stages;
+  std::vector<Stage> event_pool;
+  // workspace
+  DevBuf scalars, counts, offsets, task_offsets, tile_sums, sorted, tasks, partials, chunk_out, window_out, misc, out;
+  NttWorkspace ntt_ws;
+};
+
+namespace {
+
+#define CUDA_TRY(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);            \
+      return _e == cudaErrorMemoryAllocation ? OZL_ERR_OOM : OZL_ERR_CUDA;               \
+    }                                                                                    \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                \
+  do {                                                                                   \
+    (ctx)->launches++;                                                                   \
+    if (!(ctx)->stages.empty() && (ctx)->timing) (ctx)->stages.back().launches++;        \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->last_error = std::string("kernel launch: ") + cudaGetErrorString(_e);       \
+      return OZL_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+int ensure(ozl_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return OZL_OK;
+  if (b.p) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 16 + 256;
+  CUDA_TRY(ctx, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return OZL_OK;
+}
+
+int stage_begin(ozl_ctx* ctx, const char* name) {
+  if (!ctx->timing) return OZL_OK;
+  Stage s;
+  s.name = name;
+  CUDA_TRY(ctx, cudaEventCreate(&s.e0));
+  CUDA_TRY(ctx, cudaEventCreate(&s.e1));
+  CUDA_TRY(ctx, cudaEventRecord(s.e0, ctx->stream));
+  ctx->stages.push_back(s);
+  return OZL_OK;
+}
+int stage_end(ozl_ctx* ctx) {
+  if (!ctx->timing) return OZL_OK;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->stages.back().e1, ctx->stream));
+  return OZL_OK;
+}
+void stages_clear(ozl_ctx* ctx) {
+  for (auto& s : ctx->stages) {
+    if (s.e0) cudaEventDestroy(s.e0);
+    if (s.e1) cudaEventDestroy(s.e1);
+  }
+  ctx->stages.clear();
+}
+
+#define STAGE(ctx, name)                          \
+  do {                                            \
+    int _r = stage_begin(ctx, name);              \
+    if (_r) return _r;                            \
+  } while (0)
+#define STAGE_END(ctx)                            \
+  do {                                            \
+    int _r = stage_end(ctx);                      \
+    if (_r) return _r;                            \
+  } while (0)
+
+int coord_u32(int curve) {
+  switch (curve) {
+    case OZL_BLS12_381_G1: return 12;
+    case OZL_BLS12_381_G2: return 24;
+    case OZL_BN254_G1: return 8;
+    case OZL_BN254_G2: return 16;
+  }
+  return 0;
+}
+int scalar_bits(int curve) { return (curve == OZL_BLS12_381_G1 || curve == OZL_BLS12_381_G2) ? 255 : 254; }
+
+// Window width: minimise  W * (n * (1 + divergence) * madd + B * reduce)  in field multiplications.
+MsmPlan make_plan(int curve, size_t n, int forced_c) {
+  const int lambda = scalar_bits(curve);
+  int best_c = 4;
+  double best = 1e300;
+  for (int c = 4; c <= 22; c++) {
+    const int W = (lambda + 1 + c - 1) / c;
+    const double B = std::ldexp(1.0, c - 1);
+    const double m = std::max((double)n / B, 1e-9);
+    const double diverge = 1.0 + 2.5 / std::sqrt(std::max(m, 1.0));
+    const double cost = W * ((double)n * diverge * 10.0 + B * 30.0);
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  MsmPlan p;
+  p.c = forced_c ? forced_c : best_c;
+  p.W = (lambda + 1 + p.c - 1) / p.c;
+  p.B = 1u << (p.c - 1);
+  p.NB = (uint32_t)p.W * p.B;
+  p.lmax = 256;
+  uint32_t chunk = p.B / 1024;
+  if (chunk < 4) chunk = 4;
+  if (chunk > 64) chunk = 64;
+  if (chunk > p.B) chunk = p.B;
+  p.chunk = chunk;
+  p.K = p.B / chunk;
+  p.max_tasks = p.NB + (uint32_t)(((uint64_t)n * p.W) / p.lmax) + 1;
+  return p;
+}
+
+template <class Op>
+int run_scan(ozl_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out, Op op) {
+  const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  int r = ensure(ctx, ctx->tile_sums, (size_t)tiles * 4);
+  if (r) return r;
+  uint32_t* ts = (uint32_t*)ctx->tile_sums.p;
+  k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, ts, op);
+  LAUNCH_CHECK(ctx);
+  k_scan_tile_offsets<<<1, 1024, 0, ctx->stream>>>(ts, tiles, out + n);
+  LAUNCH_CHECK(ctx);
+  k_scan_apply<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, ts, out, op);
+  LAUNCH_CHECK(ctx);
+  return OZL_OK;
+}
+
+template <class F>
+int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
+  constexpr int XY = 4 * F::N;
+  const MsmPlan p = make_plan(b.curve, n, ctx->forced_c);
+  if ((uint64_t)n * p.W >= 0xffffffffull || n >= 0x7fffffffull) {
+    ctx->last_error = "msm: n too large for 32-bit indices";
+    return OZL_ERR_ARG;
+  }
+  int r;
+  if ((r = ensure(ctx, ctx->counts, (size_t)p.NB * 4))) return r;
+  if ((r = ensure(ctx, ctx->offsets, ((size_t)p.NB + 1) * 4))) return r;
+  if ((r = ensure(ctx, ctx->task_offsets, ((size_t)p.NB + 1) * 4))) return r;
+  if ((r = ensure(ctx, ctx->sorted, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
+  if ((r = ensure(ctx, ctx->tasks, (size_t)p.max_tasks * 8))) return r;
+  if ((r = ensure(ctx, ctx->partials, (size_t)p.max_tasks * XY * 4))) return r;
+  if ((r = ensure(ctx, ctx->chunk_out, (size_t)p.W * p.K * XY * 4))) return r;
+  if ((r = ensure(ctx, ctx->window_out, (size_t)p.W * XY * 4))) return r;
+  if ((r = ensure(ctx, ctx->misc, 64))) return r;
+
+  uint32_t* counts = (uint32_t*)ctx->counts.p;
+  uint32_t* offsets = (uint32_t*)ctx->offsets.p;
+  uint32_t* task_offsets = (uint32_t*)ctx->task_offsets.p;
+  uint32_t* sorted = (uint32_t*)ctx->sorted.p;
+  uint2* tasks = (uint2*)ctx->tasks.p;
+  uint32_t* partials = (uint32_t*)ctx->partials.p;
+  uint32_t* chunk_out = (uint32_t*)ctx->chunk_out.p;
+  uint32_t* window_out = (uint32_t*)ctx->window_out.p;
+  uint32_t* work_counter = (uint32_t*)ctx->misc.p;
+  cudaStream_t st = ctx->stream;
+  const int grid_io = ctx->sm_count * 8;
+
+  STAGE(ctx, "digits_count");
+  CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)p.NB * 4, st));
+  CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 64, st));
+  k_count<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.B, counts);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+
+  STAGE(ctx, "scan");
+  if ((r = run_scan(ctx, counts, p.NB, offsets, ScanIdentity{1}))) return r;
+  if ((r = run_scan(ctx, counts, p.NB, task_offsets, ScanCeilDiv{p.lmax}))) return r;
+  STAGE_END(ctx);
+
+  STAGE(ctx, "scatter");
+  k_scatter<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.B, offsets, counts, sorted);
+  LAUNCH_CHECK(ctx);
+  k_tasks<<<grid_io, 256, 0, st>>>(offsets, task_offsets, p.NB, p.lmax, tasks);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+
+  STAGE(ctx, "accumulate");
+  k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, tasks, task_offsets + p.NB, work_counter, partials);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+
+  STAGE(ctx, "bucket_reduce");
+  const uint32_t total_chunks = (uint32_t)p.W * p.K;
+  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, task_offsets, total_chunks, p.K, p.B, p.chunk, chunk_out);
+  LAUNCH_CHECK(ctx);
+  k_window_sum<F><<<p.W, 256, 0, st>>>(chunk_out, p.K, window_out);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+
+  STAGE(ctx, "final");
+  k_final<F><<<1, 32, 0, st>>>(window_out, p.W, p.c, d_out);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+  return OZL_OK;
+}
+
+int msm_dispatch(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
+  switch (b.curve) {
+    case OZL_BLS12_381_G1: return msm_run<Fp<Bls12381Fq>>(ctx, b, d_scalars, n, d_out);
+    case OZL_BLS12_381_G2: return msm_run<Fp2<Bls12381Fq>>(ctx, b, d_scalars, n, d_out);
+    case OZL_BN254_G1: return msm_run<Fp<Bn254Fq>>(ctx, b, d_scalars, n, d_out);
+    case OZL_BN254_G2: return msm_run<Fp2<Bn254Fq>>(ctx, b, d_scalars, n, d_out);
+  }
+  return OZL_ERR_ARG;
+}
+
+int find_bases(ozl_ctx* ctx, uint32_t handle, Bases** out) {
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end()) return OZL_ERR_HANDLE;
+  *out = &it->second;
+  return OZL_OK;
+}
+
+int alloc_bases(ozl_ctx* ctx, int curve, size_t n, bool with_inf, Bases* b) {
+  const int cu = coord_u32(curve);
+  if (!cu) return OZL_ERR_ARG;
+  b->curve = curve;
+  b->n = n;
+  CUDA_TRY(ctx, cudaMalloc((void**)&b->d_pts, std::max<size_t>(n, 1) * 2 * cu * 4));
+  if (with_inf) {
+    cudaError_t e = cudaMalloc((void**)&b->d_inf, (n + 7) / 8 + 1);
+    if (e != cudaSuccess) {
+      cudaFree(b->d_pts);
+      ctx->last_error = cudaGetErrorString(e);
+      return OZL_ERR_OOM;
+    }
+  }
+  return OZL_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int ozl_version(void) { return 100; }
+
+const char* ozl_strerror(int s) {
+  switch (s) {
+    case OZL_OK: return "ok";
+    case OZL_ERR_ARG: return "invalid argument";
+    case OZL_ERR_CUDA: return "CUDA error";
+    case OZL_ERR_NO_DEVICE: return "no usable CUDA device";
+    case OZL_ERR_OOM: return "out of memory";
+    case OZL_ERR_HANDLE: return "unknown bases handle";
+    case OZL_ERR_DOMAIN: return "domain larger than the field's two-adicity";
+  }
+  return "unknown status";
+}
+
+const char* ozl_last_error(const ozl_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int ozl_ctx_create(int device, ozl_ctx** out) {
+  if (!out) return OZL_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return OZL_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return OZL_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return OZL_ERR_NO_DEVICE;
+  ozl_ctx* ctx = new (std::nothrow) ozl_ctx();
+  if (!ctx) return OZL_ERR_OOM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return OZL_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return OZL_OK;
+}
+
+void ozl_ctx_destroy(ozl_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  stages_clear(ctx);
+  for (auto& kv : ctx->bases) {
+    cudaFree(kv.second.d_pts);
+    if (kv.second.d_inf) cudaFree(kv.second.d_inf);
+  }
+  DevBuf* bufs[] = {&ctx->scalars, &ctx->counts, &ctx->offsets, &ctx->task_offsets, &ctx->tile_sums, &ctx->sorted,
+                    &ctx->tasks, &ctx->partials, &ctx->chunk_out, &ctx->window_out, &ctx->misc, &ctx->out};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  void* nb[] = {ctx->ntt_ws.scratch, ctx->ntt_ws.tw, ctx->ntt_ws.glo, ctx->ntt_ws.ghi, ctx->ntt_ws.consts};
+  for (void* p : nb)
+    if (p) cudaFree(p);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int ozl_ctx_set_stream(ozl_ctx* ctx, void* s) {
+  if (!ctx) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return OZL_OK;
+}
+void* ozl_ctx_get_stream(ozl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int ozl_ctx_synchronize(ozl_ctx* ctx) {
+  if (!ctx) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OZL_OK;
+}
+
+int ozl_curve_coord_limbs(int curve) { return coord_u32(curve) / 2; }
+
+// ---- bases ----------------------------------------------------------------------------------
+int ozl_msm_bases_upload(ozl_ctx* ctx, int curve, const uint64_t* bases, const uint8_t* inf_mask, size_t n,
+                         uint32_t* handle) {
+  if (!ctx || !handle || (!bases && n)) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Bases b;
+  int r = alloc_bases(ctx, curve, n, inf_mask != nullptr, &b);
+  if (r) return r;
+  const size_t bytes = n * 2 * coord_u32(curve) * 4;
+  CUDA_TRY(ctx, cudaMemcpyAsync(b.d_pts, bases, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (inf_mask) CUDA_TRY(ctx, cudaMemcpyAsync(b.d_inf, inf_mask, (n + 7) / 8, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *handle = ctx->next_handle++;
+  ctx->bases[*handle] = b;
+  return OZL_OK;
+}
+
+int ozl_msm_bases_upload_device(ozl_ctx* ctx, int curve, const uint64_t* d_bases, const uint8_t* d_inf_mask, size_t n,
+                                uint32_t* handle) {
+  if (!ctx || !handle || (!d_bases && n)) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Bases b;
+  int r = alloc_bases(ctx, curve, n, d_inf_mask != nullptr, &b);
+  if (r) return r;
+  const size_t bytes = n * 2 * coord_u32(curve) * 4;
+  CUDA_TRY(ctx, cudaMemcpyAsync(b.d_pts, d_bases, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (d_inf_mask) CUDA_TRY(ctx, cudaMemcpyAsync(b.d_inf, d_inf_mask, (n + 7) / 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *handle = ctx->next_handle++;
+  ctx->bases[*handle] = b;
+  return OZL_OK;
+}
+
+int ozl_msm_bases_generate(ozl_ctx* ctx, int curve, uint64_t start, size_t n, uint32_t* handle) {
+  if (!ctx || !handle || start == 0 || n >= 0x7fffffffull) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Bases b;
+  int r = alloc_bases(ctx, curve, n, false, &b);
+  if (r) return r;
+  const uint32_t threads = (uint32_t)((n + GEN_RUN - 1) / GEN_RUN);
+  const uint32_t blocks = (threads + 127) / 128;
+  if (n) {
+    switch (curve) {
+      case OZL_BLS12_381_G1: k_generate_bases<Fp<Bls12381Fq>, Bls12381G1><<<blocks, 128, 0, ctx->stream>>>(start, (uint32_t)n, b.d_pts); break;
+      case OZL_BLS12_381_G2: k_generate_bases<Fp2<Bls12381Fq>, Bls12381G2><<<blocks, 128, 0, ctx->stream>>>(start, (uint32_t)n, b.d_pts); break;
+      case OZL_BN254_G1: k_generate_bases<Fp<Bn254Fq>, Bn254G1><<<blocks, 128, 0, ctx->stream>>>(start, (uint32_t)n, b.d_pts); break;
+      case OZL_BN254_G2: k_generate_bases<Fp2<Bn254Fq>, Bn254G2><<<blocks, 128, 0, ctx->stream>>>(start, (uint32_t)n, b.d_pts); break;
+    }
+    ctx->launches++;
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("bases_generate: ") + cudaGetErrorString(e);
+    cudaFree(b.d_pts);
+    return OZL_ERR_CUDA;
+  }
+  *handle = ctx->next_handle++;
+  ctx->bases[*handle] = b;
+  return OZL_OK;
+}
+
+int ozl_msm_bases_download(ozl_ctx* ctx, uint32_t handle, size_t first, size_t n, uint64_t* out) {
+  if (!ctx || !out) return OZL_ERR_ARG;
+  Bases* b;
+  int r = find_bases(ctx, handle, &b);
+  if (r) return r;
+  if (first + n > b->n) return OZL_ERR_ARG;
+  const size_t stride = 2 * coord_u32(b->curve);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, b->d_pts + first * stride, n * stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OZL_OK;
+}
+
+int ozl_msm_bases_free(ozl_ctx* ctx, uint32_t handle) {
+  if (!ctx) return OZL_ERR_ARG;
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end()) return OZL_ERR_HANDLE;
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(it->second.d_pts);
+  if (it->second.d_inf) cudaFree(it->second.d_inf);
+  ctx->bases.erase(it);
+  return OZL_OK;
+}
+
+// ---- msm ------------------------------------------------------------------------------------
+int ozl_msm_device_async(ozl_ctx* ctx, uint32_t handle, const uint64_t* d_scalars, size_t n, uint64_t* d_out) {
+  if (!ctx || !d_out || (!d_scalars && n)) return OZL_ERR_ARG;
+  Bases* b;
+  int r = find_bases(ctx, handle, &b);
+  if (r) return r;
+  if (n > b->n) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->timing) stages_clear(ctx);
+  return msm_dispatch(ctx, *b, (const uint32_t*)d_scalars, n, (uint32_t*)d_out);
+}
+
+int ozl_msm(ozl_ctx* ctx, uint32_t handle, const uint64_t* scalars, size_t n, uint64_t* out_jacobian) {
+  if (!ctx || !out_jacobian || (!scalars && n)) return OZL_ERR_ARG;
+  Bases* b;
+  int r = find_bases(ctx, handle, &b);
+  if (r) return r;
+  if (n > b->n) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t out_bytes = 3 * coord_u32(b->curve) * 4;
+  if ((r = ensure(ctx, ctx->scalars, std::max<size_t>(n, 1) * 32))) return r;
+  if ((r = ensure(ctx, ctx->out, 1024))) return r;
+  if (ctx->timing) stages_clear(ctx);
+  STAGE(ctx, "h2d_scalars");
+  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  STAGE_END(ctx);
+  if ((r = msm_dispatch(ctx, *b, (const uint32_t*)ctx->scalars.p, n, (uint32_t*)ctx->out.p))) return r;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_jacobian, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OZL_OK;
+}
+
+int ozl_msm_set_window_bits(ozl_ctx* ctx, int c) {
+  if (!ctx || (c != 0 && (c < 2 || c > 24))) return OZL_ERR_ARG;
+  ctx->forced_c = c;
+  return OZL_OK;
+}
+
+int ozl_msm_get_window_bits(ozl_ctx* ctx, int curve, size_t n) {
+  if (!ctx || !coord_u32(curve)) return -1;
+  return make_plan(curve, n, ctx->forced_c).c;
+}
+
+int ozl_jacobian_sum(ozl_ctx* ctx, int curve, const uint64_t* points, size_t k, uint64_t* out_jacobian) {
+  if (!ctx || !out_jacobian || (!points && k) || !coord_u32(curve)) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t pt_bytes = 3 * coord_u32(curve) * 4;
+  int r;
+  if ((r = ensure(ctx, ctx->scalars, std::max<size_t>(k, 1) * pt_bytes))) return r;
+  if ((r = ensure(ctx, ctx->out, 1024))) return r;
+  if (k) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, points, k * pt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const uint32_t* in = (const uint32_t*)ctx->scalars.p;
+  uint32_t* out = (uint32_t*)ctx->out.p;
+  switch (curve) {
+    case OZL_BLS12_381_G1: k_jacobian_sum<Fp<Bls12381Fq>><<<1, 32, 0, ctx->stream>>>(in, (uint32_t)k, out); break;
+    case OZL_BLS12_381_G2: k_jacobian_sum<Fp2<Bls12381Fq>><<<1, 32, 0, ctx->stream>>>(in, (uint32_t)k, out); break;
+    case OZL_BN254_G1: k_jacobian_sum<Fp<Bn254Fq>><<<1, 32, 0, ctx->stream>>>(in, (uint32_t)k, out); break;
+    case OZL_BN254_G2: k_jacobian_sum<Fp2<Bn254Fq>><<<1, 32, 0, ctx->stream>>>(in, (uint32_t)k, out); break;
+  }
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_jacobian, out, pt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OZL_OK;
+}
+
+int ozl_jacobian_to_affine(ozl_ctx* ctx, int curve, const uint64_t* jacobian, uint64_t* out_affine, int* is_identity) {
+  if (!ctx || !jacobian || !out_affine || !is_identity || !coord_u32(curve)) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t cu = coord_u32(curve);
+  int r;
+  if ((r = ensure(ctx, ctx->scalars, 3 * cu * 4))) return r;
+  if ((r = ensure(ctx, ctx->out, 1024))) return r;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, jacobian, 3 * cu * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const uint32_t* in = (const uint32_t*)ctx->scalars.p;
+  uint32_t* out = (uint32_t*)ctx->out.p;
+  int* flag = (int*)((char*)ctx->out.p + 512);
+  switch (curve) {
+    case OZL_BLS12_381_G1: k_jacobian_to_affine<Fp<Bls12381Fq>><<<1, 32, 0, ctx->stream>>>(in, out, flag); break;
+    case OZL_BLS12_381_G2: k_jacobian_to_affine<Fp2<Bls12381Fq>><<<1, 32, 0, ctx->stream>>>(in, out, flag); break;
+    case OZL_BN254_G1: k_jacobian_to_affine<Fp<Bn254Fq>><<<1, 32, 0, ctx->stream>>>(in, out, flag); break;
+    case OZL_BN254_G2: k_jacobian_to_affine<Fp2<Bn254Fq>><<<1, 32, 0, ctx->stream>>>(in, out, flag); break;
+  }
+  LAUNCH_CHECK(ctx);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_affine, out, 2 * cu * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(is_identity, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OZL_OK;
+}
+
+// ---- ntt ------------------------------------------------------------------------------------
+int ozl_ntt_device_async(ozl_ctx* ctx, int field, uint64_t* d_data, uint32_t log_n, int inverse, int coset) {
+  if (!ctx || !d_data) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->timing) stages_clear(ctx);
+  int launches = 0;
+  int r = OZL_ERR_ARG;
+  STAGE(ctx, "ntt");
+  if (field == OZL_BN254_FR) r = ntt_run<Bn254Fr>(ctx->stream, ctx->ntt_ws, field, (uint32_t*)d_data, log_n, inverse != 0, coset != 0, &launches);
+  else if (field == OZL_BLS12_381_FR) r = ntt_run<Bls12381Fr>(ctx->stream, ctx->ntt_ws, field, (uint32_t*)d_data, log_n, inverse != 0, coset != 0, &launches);
+  ctx->launches += launches;
+  if (ctx->timing && !ctx->stages.empty()) ctx->stages.back().launches += launches;
+  STAGE_END(ctx);
+  if (r == -2) return OZL_ERR_DOMAIN;
+  if (r == -4) return OZL_ERR_OOM;
+  if (r == -3) {
+    ctx->last_error = std::string("ntt launch: ") + cudaGetErrorString(cudaGetLastError());
+    return OZL_ERR_CUDA;
+  }
+  return r;
+}
+
+int ozl_ntt(ozl_ctx* ctx, int field, uint64_t* data, uint32_t log_n, int inverse, int coset) {
+  if (!ctx || !data) return OZL_ERR_ARG;
+  if (field != OZL_BN254_FR && field != OZL_BLS12_381_FR) return OZL_ERR_ARG;
+  if (log_n > (uint32_t)(field == OZL_BN254_FR ? Bn254Fr::TWO_ADICITY : Bls12381Fr::TWO_ADICITY)) return OZL_ERR_DOMAIN;
+  if (log_n > 30) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t bytes = ((size_t)1 << log_n) * 32;
+  int r;
+  if ((r = ensure(ctx, ctx->scalars, bytes))) return r;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if ((r = ozl_ntt_device_async(ctx, field, (uint64_t*)ctx->scalars.p, log_n, inverse, coset))) return r;
+  CUDA_TRY(ctx, cudaMemcpyAsync(data, ctx->scalars.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OZL_OK;
+}
+
+// ---- instrumentation ------------------------------------------------------------------------
+int ozl_ctx_enable_timing(ozl_ctx* ctx, int on) {
+  if (!ctx) return OZL_ERR_ARG;
+  ctx->timing = on != 0;
+  if (!on) stages_clear(ctx);
+  return OZL_OK;
+}
+
+int ozl_ctx_get_stage_times(ozl_ctx* ctx, ozl_stage_time* out, int cap) {
+  if (!ctx || !out) return -1;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+  int k = 0;
+  for (auto& s : ctx->stages) {
+    if (k >= cap) break;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.e0, s.e1) != cudaSuccess) ms = -1.f;
+    memset(&out[k], 0, sizeof(out[k]));
+    snprintf(out[k].name, sizeof(out[k].name), "%s", s.name.c_str());
+    out[k].ms = ms;
+    out[k].launches = s.launches;
+    k++;
+  }
+  return k;
+}
+
+uint64_t ozl_ctx_launch_count(const ozl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ozl_bench_field_mul(ozl_ctx* ctx, int field_id, int iters, double* mul_per_sec) {
+  if (!ctx || !mul_per_sec || iters <= 0) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int r;
+  if ((r = ensure(ctx, ctx->out, 1024))) return r;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(ctx, cudaEventCreate(&e0));
+  CUDA_TRY(ctx, cudaEventCreate(&e1));
+  const int blocks = ctx->sm_count * 8, threads = 128;
+  for (int rep = 0; rep < 2; rep++) {
+    if (rep == 1) CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    if (field_id == 0) k_bench_mul<Fp<Bls12381Fq>><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->out.p, iters);
+    else if (field_id == 1) k_bench_mul<Fp<Bn254Fq>><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)ctx->out.p, iters);
+    else return OZL_ERR_ARG;
+    LAUNCH_CHECK(ctx);
+  }
+  CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *mul_per_sec = (double)blocks * threads * iters * 4.0 / (ms * 1e-3);
+  return OZL_OK;
+}
+
+}  // extern "C"

@@ -37,7 +37,7 @@ struct XYZZ {
   OZL_DEV XYZZ neg() const { XYZZ r = *this; r.y = y.neg(); return r; }
 
   // 2 * (affine p), mdbl-2008-s with a = 0
-  static OZL_DEV XYZZ dbl_affine(const Affine<F>& p) {
+  static OZL_DEV_NOINLINE XYZZ dbl_affine(const Affine<F>& p) {
     XYZZ r;
     F u = p.y.dbl();
     F v = u.sqr();
@@ -53,7 +53,7 @@ struct XYZZ {
   }
 
   // dbl-2008-s with a = 0
-  OZL_DEV XYZZ dbl() const {
+  OZL_DEV_NOINLINE XYZZ dbl() const {
     if (is_identity()) return *this;
     XYZZ r;
     F u = y.dbl();
@@ -97,8 +97,11 @@ struct XYZZ {
     zzz = zzz * p3;
   }
 
+  // out-of-line copy of add_mixed for cold kernels (keeps their code size small)
+  OZL_DEV_NOINLINE void add_mixed_cold(const Affine<F>& p) { add_mixed(p); }
+
   // this += o (add-2008-s)
-  OZL_DEV void add(const XYZZ& o) {
+  OZL_DEV_NOINLINE void add(const XYZZ& o) {
     if (o.is_identity()) return;
     if (is_identity()) {
       *this = o;
@@ -129,7 +132,7 @@ struct XYZZ {
   }
 
   // [k] * this for a small unsigned k (left-to-right double-and-add); cold path.
-  OZL_DEV XYZZ mul_u32(uint32_t k) const {
+  OZL_DEV_NOINLINE XYZZ mul_u32(uint32_t k) const {
     XYZZ acc = identity();
     for (int bit = 31; bit >= 0; bit--) {
       acc = acc.dbl();
@@ -150,7 +153,7 @@ struct XYZZ {
   }
 
   // affine (x, y); returns false for the identity
-  OZL_DEV bool to_affine(Affine<F>& p) const {
+  OZL_DEV_NOINLINE bool to_affine(Affine<F>& p) const {
     if (is_identity()) return false;
     F zi = zzz.inverse();          // 1/Z^3
     F zi2 = (zi * zz).sqr();       // (1/Z)^2 = (ZZ/ZZZ)^2

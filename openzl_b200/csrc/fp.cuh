@@ -202,7 +202,7 @@ struct Fp {
   OZL_DEV Fp to_mont() const { return *this * r2(); }
 
   // a^(p-2) by square-and-multiply over the bits of p - 2 (cold path: affine conversion).
-  OZL_DEV Fp inverse() const {
+  OZL_DEV_NOINLINE Fp inverse() const {
     uint32_t e[N];
     e[0] = ptx::sub_cc(P::mod()[0], 2);
 #pragma unroll

@@ -15,12 +15,14 @@
 #if defined(__CUDACC__)
 #define OZL_DEV __device__ __forceinline__
 #define OZL_HOSTDEV __host__ __device__ __forceinline__
+#define OZL_DEV_NOINLINE __device__ __noinline__
 #else
 #ifndef OZL_HOST_EMU
 #error "ptx.cuh needs nvcc (or -DOZL_HOST_EMU for the g++ test build)"
 #endif
 #define OZL_DEV inline
 #define OZL_HOSTDEV inline
+#define OZL_DEV_NOINLINE inline
 #endif
 
 namespace ozl {

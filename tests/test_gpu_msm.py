@@ -1,0 +1,209 @@
+"""-m gpu parity tests of the MSM path, through the C ABI, against the CPU oracle.
+
+Contract under test: ark_ec::msm::VariableBaseMSM::multi_scalar_mul as called behind
+/root/reference/plugins/arkworks/src/groth16.rs:454.  Bit-exact: affine (x, y) Montgomery limbs
+of the GPU result equal the oracle's (Jacobian representatives are not unique, so comparison is
+after into_affine, as SURVEY.md section 7 prescribes).
+"""
+import numpy as np
+import pytest
+
+import openzl_b200 as ozl
+from oracle import cbind, curves
+from tests.util import ints_to_array, limbs_to_int, random_scalars
+
+pytestmark = pytest.mark.gpu
+
+CURVES = ["bls12_381_g1", "bn254_g1", "bls12_381_g2", "bn254_g2"]
+
+
+def oracle_affine(name, bases, scalars, inf=None, threads=8):
+    return cbind.to_affine(name, cbind.msm(name, bases, scalars, inf=inf, threads=threads))
+
+
+def gpu_affine(ctx, name, jac):
+    aff, is_inf = ctx.jacobian_to_affine(ozl.CURVE_IDS[name], jac)
+    # cross-check the device normalisation with the oracle's
+    o_aff, o_inf = cbind.to_affine(name, jac)
+    assert is_inf == o_inf
+    assert (aff == o_aff).all()
+    return aff, is_inf
+
+
+def directed_scalars(name, n, seed):
+    c = curves.CURVES[name]
+    r = c.fr.p
+    s = random_scalars(n, r, seed)
+    special = [0, 1, 2, r - 1, r - 2, (1 << 16) - 1, 1 << 16, (1 << 15), (1 << 15) + 1, (1 << 254) - 1 if r > (1 << 254) else (1 << 253) - 1,
+               (r - 1) // 2, (r + 1) // 2, 0xFFFF_FFFF, 1 << 32, (1 << 64) - 1, 1 << 64]
+    for i, v in enumerate(special):
+        s[i] = ints_to_array([v % r])[0]
+    return s
+
+
+@pytest.mark.parametrize("name", CURVES)
+def test_msm_2_12_parity(ctx, name):
+    """BASELINE config 1: 2^12 points, seeded random + directed scalars, directed points."""
+    n = 1 << 12 if name.endswith("g1") else 1 << 10
+    bases = cbind.bases_seq(name, 1, n)
+    # directed points: a duplicate, P and -P, and (below) an infinity entry
+    bases[5] = bases[4]
+    c = curves.CURVES[name]
+    L = cbind.COORD_LIMBS[name]
+    P7 = c.affine_from_mont_limbs(list(bases[7]))
+    bases[8] = np.array(c.affine_to_mont_limbs(c.neg(P7)), dtype=np.uint64)
+    scalars = directed_scalars(name, n, seed=0x4F5A4C5F)
+    scalars[5] = scalars[4]          # P + P inside one bucket -> doubling branch
+    scalars[8] = scalars[7]          # P + (-P) inside one bucket -> identity branch
+    inf = np.zeros((n + 7) // 8, dtype=np.uint8)
+    inf[20 >> 3] |= 1 << (20 & 7)
+    exp, exp_inf = oracle_affine(name, bases, scalars, inf=inf)
+    h = ctx.upload_bases(ozl.CURVE_IDS[name], bases, inf)
+    try:
+        got, got_inf = gpu_affine(ctx, name, h.msm(scalars))
+    finally:
+        h.free()
+    assert got_inf == exp_inf
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("c_bits", [4, 7, 10, 13, 16])
+def test_msm_window_sweep(ctx, c_bits):
+    name = "bls12_381_g1"
+    n = 3000
+    bases = cbind.bases_seq(name, 3, n)
+    scalars = directed_scalars(name, n, seed=c_bits)
+    exp, _ = oracle_affine(name, bases, scalars)
+    h = ctx.upload_bases(ozl.BLS12_381_G1, bases)
+    try:
+        ctx.set_window_bits(c_bits)
+        got, _ = gpu_affine(ctx, name, h.msm(scalars))
+    finally:
+        ctx.set_window_bits(0)
+        h.free()
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 257])
+def test_msm_ragged_sizes(ctx, n):
+    name = "bn254_g1"
+    bases = cbind.bases_seq(name, 1, max(n, 1))
+    scalars = random_scalars(max(n, 1), curves.CURVES[name].fr.p, seed=n + 1)
+    h = ctx.upload_bases(ozl.BN254_G1, bases)
+    try:
+        jac = h.msm(scalars[:n])
+    finally:
+        h.free()
+    got, got_inf = gpu_affine(ctx, name, jac)
+    if n == 0:
+        assert got_inf
+        # ark GroupProjective::zero() = (0, 1, 0)
+        assert limbs_to_int(jac[8:12]) == 0 and limbs_to_int(jac[0:4]) == 0
+        return
+    exp, exp_inf = oracle_affine(name, bases[:n], scalars[:n])
+    assert got_inf == exp_inf and (got == exp).all()
+
+
+def test_msm_all_zero_and_all_one_scalars(ctx):
+    name = "bls12_381_g1"
+    n = 5000
+    bases = cbind.bases_seq(name, 1, n)
+    h = ctx.upload_bases(ozl.BLS12_381_G1, bases)
+    try:
+        zero = np.zeros((n, 4), dtype=np.uint64)
+        _, is_inf = gpu_affine(ctx, name, h.msm(zero))
+        assert is_inf
+        one = zero.copy()
+        one[:, 0] = 1          # every point lands in one bucket: exercises the task splitter
+        got, _ = gpu_affine(ctx, name, h.msm(one))
+        exp, _ = oracle_affine(name, bases, one)
+        assert (got == exp).all()
+        # sum_{i<n} (i+1) G = [n(n+1)/2] G
+        k = n * (n + 1) // 2
+        assert (got == cbind.to_affine(name, cbind.gen_mul(name, k))[0]).all()
+    finally:
+        h.free()
+
+
+def test_msm_skewed_small_scalars(ctx):
+    """Witness-like distribution: mostly 0/1/small values plus a few full-width ones."""
+    name = "bn254_g1"
+    n = 1 << 14
+    r = curves.CURVES[name].fr.p
+    rng = np.random.default_rng(7)
+    scalars = np.zeros((n, 4), dtype=np.uint64)
+    scalars[:, 0] = rng.integers(0, 3, size=n, dtype=np.uint64)
+    full = random_scalars(n // 16, r, seed=8)
+    scalars[:: 16] = full
+    bases = cbind.bases_seq(name, 11, n)
+    exp, _ = oracle_affine(name, bases, scalars)
+    h = ctx.upload_bases(ozl.BN254_G1, bases)
+    try:
+        got, _ = gpu_affine(ctx, name, h.msm(scalars))
+    finally:
+        h.free()
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("name", CURVES)
+def test_generated_bases_match_oracle(ctx, name):
+    n = 1000
+    h = ctx.generate_bases(ozl.CURVE_IDS[name], 5, n)
+    try:
+        got = h.download()
+    finally:
+        h.free()
+    exp = cbind.bases_seq(name, 5, n)
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_msm_known_dlog_large(ctx, log_n):
+    """Size-independent property: for P_i = [i+1]G, sum s_i P_i = [sum s_i (i+1) mod r] G."""
+    name = "bls12_381_g1"
+    n = 1 << log_n
+    r = curves.CURVES[name].fr.p
+    scalars = random_scalars(n, r, seed=log_n)
+    h = ctx.generate_bases(ozl.BLS12_381_G1, 1, n)
+    try:
+        got, _ = gpu_affine(ctx, name, h.msm(scalars))
+    finally:
+        h.free()
+    k = cbind.dot_mod_r("bls12_381_fr", scalars, np.arange(1, n + 1, dtype=np.uint64))
+    exp, _ = cbind.to_affine(name, cbind.gen_mul(name, k))
+    assert (got == exp).all()
+
+
+def test_reference_interface(ctx):
+    """VariableBaseMSM::multi_scalar_mul mirror: size = min(len(bases), len(scalars))."""
+    name = "bn254_g1"
+    bases = cbind.bases_seq(name, 1, 100)
+    scalars = random_scalars(80, curves.CURVES[name].fr.p, seed=3)
+    res = ozl.ec.VariableBaseMSM.multi_scalar_mul(bases, scalars, curve=ozl.BN254_G1, ctx=ctx)
+    got, inf = res.into_affine()
+    exp, _ = oracle_affine(name, bases[:80], scalars)
+    assert not inf and (got == exp).all()
+
+
+def test_jacobian_sum(ctx):
+    name = "bls12_381_g1"
+    ks = [5, 7, 0, 11]
+    pts = np.stack([cbind.gen_mul(name, k) for k in ks])
+    out = ctx.jacobian_sum(ozl.BLS12_381_G1, pts)
+    got, _ = cbind.to_affine(name, out)
+    exp, _ = cbind.to_affine(name, cbind.gen_mul(name, sum(ks)))
+    assert (got == exp).all()
+
+
+def test_error_paths(ctx):
+    with pytest.raises(ozl.OzlError):
+        ctx.upload_bases(99, np.zeros((1, 12), dtype=np.uint64))
+    with pytest.raises(ozl.OzlError):
+        ctx.upload_bases(ozl.BLS12_381_G1, np.zeros((1, 8), dtype=np.uint64))
+    h = ctx.upload_bases(ozl.BN254_G1, cbind.bases_seq("bn254_g1", 1, 4))
+    with pytest.raises(ozl.OzlError):
+        h.msm(np.zeros((5, 4), dtype=np.uint64))      # more scalars than bases on a handle
+    h.free()
+    with pytest.raises(ozl.OzlError):
+        h2 = ozl.Bases(ctx, 12345, ozl.BN254_G1, 4)
+        h2.msm(np.zeros((1, 4), dtype=np.uint64))

@@ -1,0 +1,71 @@
+"""-m gpu parity tests of the NTT path through the C ABI against the CPU oracle
+(ark_poly Radix2EvaluationDomain semantics; bit-exact Montgomery limbs)."""
+import numpy as np
+import pytest
+
+import openzl_b200 as ozl
+from oracle import cbind, fields
+from tests.util import random_scalars
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = [("bn254_fr", ozl.BN254_FR), ("bls12_381_fr", ozl.BLS12_381_FR)]
+MODES = [(False, False), (True, False), (False, True), (True, True)]
+
+
+@pytest.mark.parametrize("fname,fid", FIELDS)
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 6, 7, 10, 13])
+@pytest.mark.parametrize("inverse,coset", MODES)
+def test_ntt_matches_oracle(ctx, fname, fid, log_n, inverse, coset):
+    f = fields.FIELDS[fname]
+    n = 1 << log_n
+    x = random_scalars(n, f.p, seed=log_n * 4 + inverse * 2 + coset)   # any residues < p are valid Montgomery limbs
+    exp = cbind.ntt(fname, x, inverse=inverse, coset=coset)
+    got = x.copy()
+    ctx.ntt(fid, got, inverse=inverse, coset=coset)
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("fname,fid", FIELDS)
+def test_ntt_round_trip_2_20(ctx, fname, fid):
+    f = fields.FIELDS[fname]
+    n = 1 << 20
+    x = random_scalars(n, f.p, seed=99)
+    y = x.copy()
+    ctx.ntt(fid, y)
+    assert not (y == x).all()
+    # spot-check 4 outputs by direct evaluation X[k] = sum_j x[j] w^(jk) is O(n) each in Python: too slow at 2^20;
+    # instead compare a full transform at 2^16 with the oracle and the round trip here
+    ctx.ntt(fid, y, inverse=True)
+    assert (y == x).all()
+    ctx.ntt(fid, y, coset=True)
+    ctx.ntt(fid, y, inverse=True, coset=True)
+    assert (y == x).all()
+
+
+def test_ntt_2_16_vs_oracle(ctx):
+    f = fields.BN254_FR
+    x = random_scalars(1 << 16, f.p, seed=5)
+    exp = cbind.ntt("bn254_fr", x)
+    got = x.copy()
+    ctx.ntt(ozl.BN254_FR, got)
+    assert (got == exp).all()
+
+
+def test_domain_interface(ctx):
+    d = ozl.poly.Radix2EvaluationDomain.new(ozl.BN254_FR, 1000, ctx=ctx)
+    assert d.size() == 1024
+    assert ozl.poly.Radix2EvaluationDomain.new(ozl.BN254_FR, (1 << 28) + 1, ctx=ctx) is None
+    f = fields.BN254_FR
+    x = random_scalars(1000, f.p, seed=1)          # shorter than the domain: zero-extended like ark
+    padded = np.zeros((1024, 4), dtype=np.uint64)
+    padded[:1000] = x
+    assert (d.fft(x) == cbind.ntt("bn254_fr", padded)).all()
+    assert (d.coset_ifft(d.coset_fft(x)) == padded).all()
+
+
+def test_ntt_domain_error(ctx):
+    import ctypes
+    lib = ozl._lib.load()
+    buf = np.zeros((2, 4), dtype=np.uint64)
+    assert lib.ozl_ntt(ctx._h, ozl.BN254_FR, buf.ctypes.data, 29, 0, 0) == 6   # OZL_ERR_DOMAIN
