@@ -1,0 +1,26 @@
+// Defines the OzlCurveOps table for one curve: include after defining OZL_F (coordinate field),
+// OZL_C (curve constants), OZL_BASE (base prime field) and OZL_OPS (table symbol).
+#include "runtime.cuh"
+
+namespace {
+typedef OZL_F F_;
+typedef OZL_C C_;
+int msm_entry(ozl_ctx* ctx, const ozl_rt::Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
+  return ozl_rt::msm_run<F_>(ctx, b, d_scalars, n, d_out);
+}
+void generate_entry(cudaStream_t st, uint64_t start, uint32_t n, uint32_t* d_pts) {
+  const uint32_t threads = (n + GEN_RUN - 1) / GEN_RUN;
+  k_generate_bases<F_, C_><<<(threads + 127) / 128, 128, 0, st>>>(start, n, d_pts);
+}
+void jsum_entry(cudaStream_t st, const uint32_t* d_pts, uint32_t k, uint32_t* d_out) {
+  k_jacobian_sum<F_><<<1, 32, 0, st>>>(d_pts, k, d_out);
+}
+void jaff_entry(cudaStream_t st, const uint32_t* d_jac, uint32_t* d_out, int* d_flag) {
+  k_jacobian_to_affine<F_><<<1, 32, 0, st>>>(d_jac, d_out, d_flag);
+}
+void bench_entry(cudaStream_t st, int blocks, int threads, uint32_t* d_out, int iters) {
+  k_bench_mul<Fp<OZL_BASE>><<<blocks, threads, 0, st>>>(d_out, iters);
+}
+}  // namespace
+
+const OzlCurveOps OZL_OPS = {msm_entry, generate_entry, jsum_entry, jaff_entry, bench_entry};

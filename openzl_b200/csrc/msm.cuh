@@ -60,7 +60,7 @@ __device__ __forceinline__ void for_each_digit(const uint32_t* __restrict__ s, i
   }
 }
 
-__global__ void k_count(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t n,
+static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t n,
                         int c, int W, uint32_t B, uint32_t* __restrict__ counts) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (inf_mask && ((inf_mask[i >> 3] >> (i & 7)) & 1)) continue;
@@ -72,7 +72,7 @@ __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8_t* __r
   }
 }
 
-__global__ void k_scatter(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t n,
+static __global__ void k_scatter(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t n,
                           int c, int W, uint32_t B, const uint32_t* __restrict__ offsets,
                           uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -150,7 +150,7 @@ __global__ void k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n, ui
 }
 
 // single block: exclusive scan of tile_sums[0..m) in place; writes the grand total to *grand
-__global__ void k_scan_tile_offsets(uint32_t* __restrict__ tile_sums, uint32_t m, uint32_t* __restrict__ grand) {
+static __global__ void k_scan_tile_offsets(uint32_t* __restrict__ tile_sums, uint32_t m, uint32_t* __restrict__ grand) {
   __shared__ uint32_t total;
   const uint32_t per = (m + blockDim.x - 1) / blockDim.x;
   const uint32_t lo = threadIdx.x * per;
@@ -193,7 +193,7 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const 
 // ---------------------------------------------------------------------------------------------
 // tasks
 // ---------------------------------------------------------------------------------------------
-__global__ void k_tasks(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_offsets, uint32_t NB,
+static __global__ void k_tasks(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_offsets, uint32_t NB,
                         uint32_t lmax, uint2* __restrict__ tasks) {
   for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < NB; g += gridDim.x * blockDim.x) {
     const uint32_t start = offsets[g], cnt = offsets[g + 1] - start;

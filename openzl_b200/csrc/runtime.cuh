@@ -1,0 +1,261 @@
+// Host-side runtime shared by every translation unit of libozl_b200: context, device workspace,
+// bases registry, window planning, kernel sequencing and stage timing.  No CPU compute path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ozl.h"
+#include "params_gen.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "curve_ops.h"
+
+using namespace ozl;
+using namespace ozl_params;
+
+namespace ozl_rt {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct Bases {
+  int curve = -1;
+  size_t n = 0;
+  uint32_t* d_pts = nullptr;   // n * 2 * coord_u32
+  uint8_t* d_inf = nullptr;    // optional bitset
+};
+
+struct Stage {
+  std::string name;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int launches = 0;
+};
+
+}  // namespace ozl_rt
+using namespace ozl_rt;
+
+struct ozl_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  std::map<uint32_t, Bases> bases;
+  uint32_t next_handle = 1;
+  int forced_c = 0;
+  uint64_t launches = 0;
+  bool timing = false;
+  std::vector<Stage> stages;
+  std::vector<Stage> event_pool;
+  // workspace
+  DevBuf scalars, counts, offsets, task_offsets, tile_sums, sorted, tasks, partials, chunk_out, window_out, misc, out;
+  NttWorkspace ntt_ws;
+};
+
+namespace ozl_rt {
+
+#define CUDA_TRY(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);            \
+      return _e == cudaErrorMemoryAllocation ? OZL_ERR_OOM : OZL_ERR_CUDA;               \
+    }                                                                                    \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                \
+  do {                                                                                   \
+    (ctx)->launches++;                                                                   \
+    if (!(ctx)->stages.empty() && (ctx)->timing) (ctx)->stages.back().launches++;        \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->last_error = std::string("kernel launch: ") + cudaGetErrorString(_e);       \
+      return OZL_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+inline int ensure(ozl_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return OZL_OK;
+  if (b.p) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 16 + 256;
+  CUDA_TRY(ctx, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return OZL_OK;
+}
+
+inline int stage_begin(ozl_ctx* ctx, const char* name) {
+  if (!ctx->timing) return OZL_OK;
+  Stage s;
+  s.name = name;
+  CUDA_TRY(ctx, cudaEventCreate(&s.e0));
+  CUDA_TRY(ctx, cudaEventCreate(&s.e1));
+  CUDA_TRY(ctx, cudaEventRecord(s.e0, ctx->stream));
+  ctx->stages.push_back(s);
+  return OZL_OK;
+}
+inline int stage_end(ozl_ctx* ctx) {
+  if (!ctx->timing) return OZL_OK;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->stages.back().e1, ctx->stream));
+  return OZL_OK;
+}
+inline void stages_clear(ozl_ctx* ctx) {
+  for (auto& s : ctx->stages) {
+    if (s.e0) cudaEventDestroy(s.e0);
+    if (s.e1) cudaEventDestroy(s.e1);
+  }
+  ctx->stages.clear();
+}
+
+#define STAGE(ctx, name)                          \
+  do {                                            \
+    int _r = stage_begin(ctx, name);              \
+    if (_r) return _r;                            \
+  } while (0)
+#define STAGE_END(ctx)                            \
+  do {                                            \
+    int _r = stage_end(ctx);                      \
+    if (_r) return _r;                            \
+  } while (0)
+
+inline int coord_u32(int curve) {
+  switch (curve) {
+    case OZL_BLS12_381_G1: return 12;
+    case OZL_BLS12_381_G2: return 24;
+    case OZL_BN254_G1: return 8;
+    case OZL_BN254_G2: return 16;
+  }
+  return 0;
+}
+inline int scalar_bits(int curve) { return (curve == OZL_BLS12_381_G1 || curve == OZL_BLS12_381_G2) ? 255 : 254; }
+
+// Window width: minimise  W * (n * (1 + divergence) * madd + B * reduce)  in field multiplications.
+inline MsmPlan make_plan(int curve, size_t n, int forced_c) {
+  const int lambda = scalar_bits(curve);
+  int best_c = 4;
+  double best = 1e300;
+  for (int c = 4; c <= 22; c++) {
+    const int W = (lambda + 1 + c - 1) / c;
+    const double B = std::ldexp(1.0, c - 1);
+    const double m = std::max((double)n / B, 1e-9);
+    const double diverge = 1.0 + 2.5 / std::sqrt(std::max(m, 1.0));
+    const double cost = W * ((double)n * diverge * 10.0 + B * 30.0);
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  MsmPlan p;
+  p.c = forced_c ? forced_c : best_c;
+  p.W = (lambda + 1 + p.c - 1) / p.c;
+  p.B = 1u << (p.c - 1);
+  p.NB = (uint32_t)p.W * p.B;
+  p.lmax = 256;
+  uint32_t chunk = p.B / 1024;
+  if (chunk < 4) chunk = 4;
+  if (chunk > 64) chunk = 64;
+  if (chunk > p.B) chunk = p.B;
+  p.chunk = chunk;
+  p.K = p.B / chunk;
+  p.max_tasks = p.NB + (uint32_t)(((uint64_t)n * p.W) / p.lmax) + 1;
+  return p;
+}
+
+template <class Op>
+int run_scan(ozl_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out, Op op) {
+  const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  int r = ensure(ctx, ctx->tile_sums, (size_t)tiles * 4);
+  if (r) return r;
+  uint32_t* ts = (uint32_t*)ctx->tile_sums.p;
+  k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, ts, op);
+  LAUNCH_CHECK(ctx);
+  k_scan_tile_offsets<<<1, 1024, 0, ctx->stream>>>(ts, tiles, out + n);
+  LAUNCH_CHECK(ctx);
+  k_scan_apply<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, ts, out, op);
+  LAUNCH_CHECK(ctx);
+  return OZL_OK;
+}
+
+template <class F>
+int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
+  constexpr int XY = 4 * F::N;
+  const MsmPlan p = make_plan(b.curve, n, ctx->forced_c);
+  if ((uint64_t)n * p.W >= 0xffffffffull || n >= 0x7fffffffull) {
+    ctx->last_error = "msm: n too large for 32-bit indices";
+    return OZL_ERR_ARG;
+  }
+  int r;
+  if ((r = ensure(ctx, ctx->counts, (size_t)p.NB * 4))) return r;
+  if ((r = ensure(ctx, ctx->offsets, ((size_t)p.NB + 1) * 4))) return r;
+  if ((r = ensure(ctx, ctx->task_offsets, ((size_t)p.NB + 1) * 4))) return r;
+  if ((r = ensure(ctx, ctx->sorted, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
+  if ((r = ensure(ctx, ctx->tasks, (size_t)p.max_tasks * 8))) return r;
+  if ((r = ensure(ctx, ctx->partials, (size_t)p.max_tasks * XY * 4))) return r;
+  if ((r = ensure(ctx, ctx->chunk_out, (size_t)p.W * p.K * XY * 4))) return r;
+  if ((r = ensure(ctx, ctx->window_out, (size_t)p.W * XY * 4))) return r;
+  if ((r = ensure(ctx, ctx->misc, 64))) return r;
+
+  uint32_t* counts = (uint32_t*)ctx->counts.p;
+  uint32_t* offsets = (uint32_t*)ctx->offsets.p;
+  uint32_t* task_offsets = (uint32_t*)ctx->task_offsets.p;
+  uint32_t* sorted = (uint32_t*)ctx->sorted.p;
+  uint2* tasks = (uint2*)ctx->tasks.p;
+  uint32_t* partials = (uint32_t*)ctx->partials.p;
+  uint32_t* chunk_out = (uint32_t*)ctx->chunk_out.p;
+  uint32_t* window_out = (uint32_t*)ctx->window_out.p;
+  uint32_t* work_counter = (uint32_t*)ctx->misc.p;
+  cudaStream_t st = ctx->stream;
+  const int grid_io = ctx->sm_count * 8;
+
+  STAGE(ctx, "digits_count");
+  CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)p.NB * 4, st));
+  CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 64, st));
+  k_count<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.B, counts);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+
+  STAGE(ctx, "scan");
+  if ((r = run_scan(ctx, counts, p.NB, offsets, ScanIdentity{1}))) return r;
+  if ((r = run_scan(ctx, counts, p.NB, task_offsets, ScanCeilDiv{p.lmax}))) return r;
+  STAGE_END(ctx);
+
+  STAGE(ctx, "scatter");
+  k_scatter<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.B, offsets, counts, sorted);
+  LAUNCH_CHECK(ctx);
+  k_tasks<<<grid_io, 256, 0, st>>>(offsets, task_offsets, p.NB, p.lmax, tasks);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+
+  STAGE(ctx, "accumulate");
+  k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, tasks, task_offsets + p.NB, work_counter, partials);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+
+  STAGE(ctx, "bucket_reduce");
+  const uint32_t total_chunks = (uint32_t)p.W * p.K;
+  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, task_offsets, total_chunks, p.K, p.B, p.chunk, chunk_out);
+  LAUNCH_CHECK(ctx);
+  k_window_sum<F><<<p.W, 256, 0, st>>>(chunk_out, p.K, window_out);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+
+  STAGE(ctx, "final");
+  k_final<F><<<1, 32, 0, st>>>(window_out, p.W, p.c, d_out);
+  LAUNCH_CHECK(ctx);
+  STAGE_END(ctx);
+  return OZL_OK;
+}
+
+}  // namespace ozl_rt
