@@ -213,7 +213,7 @@ def run_ours(args):
     h_scalars = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
     h_scalars.copy_(d_scalars)
     d_out = torch.zeros(18, dtype=torch.int64, device=dev)
-    gathered = torch.zeros((world, 18), dtype=torch.int64, device=dev) if world > 1 else None
+    gathered = torch.zeros(world * 18, dtype=torch.int64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB); inputs are >> L2 anyway
     launches0 = ctx.launch_count
 
@@ -224,7 +224,7 @@ def run_ours(args):
 
     def combine():
         if world > 1:
-            pts = gathered.cpu().numpy().view(np.uint64)
+            pts = gathered.cpu().numpy().view(np.uint64).reshape(world, 18)
             return ctx.jacobian_sum(curve, pts)
         return d_out.cpu().numpy().view(np.uint64)
 
