@@ -96,8 +96,8 @@ void ozl_ctx_destroy(ozl_ctx* ctx) {
     cudaFree(kv.second.d_pts);
     if (kv.second.d_inf) cudaFree(kv.second.d_inf);
   }
-  DevBuf* bufs[] = {&ctx->scalars, &ctx->counts, &ctx->offsets, &ctx->task_offsets, &ctx->tile_sums, &ctx->sorted,
-                    &ctx->tasks, &ctx->partials, &ctx->chunk_out, &ctx->window_out, &ctx->misc, &ctx->out};
+  DevBuf* bufs[] = {&ctx->scalars, &ctx->counts, &ctx->offsets, &ctx->tile_sums, &ctx->sorted,
+                    &ctx->partials, &ctx->chunk_out, &ctx->window_out, &ctx->misc, &ctx->out};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   void* nb[] = {ctx->ntt_ws.scratch, ctx->ntt_ws.tw, ctx->ntt_ws.glo, ctx->ntt_ws.ghi, ctx->ntt_ws.consts};

@@ -6,10 +6,10 @@
 // sum_i s_i P_i); different schedule, chosen for a 148-SM GPU instead of <= 17 rayon tasks:
 //
 //   k_count      scalars -> signed c-bit digits, histogram of (window, bucket)       [HBM/L2 atomics]
-//   scan x2      bucket offsets, task offsets                                       [HBM]
+//   scan         bucket offsets                                                     [HBM]
 //   k_scatter    counting-sort point indices by (window, bucket)                    [HBM/L2 atomics]
-//   k_tasks      split every bucket into tasks of <= lmax points                    [HBM]
-//   k_accumulate one thread per task: gather affine points, XYZZ mixed adds         [fma pipe]  <- dominant
+//   k_accumulate one thread per fixed-length slice of the sorted indices: gather
+//                affine points, XYZZ mixed adds, flush at bucket boundaries         [fma pipe]  <- dominant
 //   k_bucket_reduce  per chunk of buckets: running sum  sum (b+1) B_b               [fma pipe]
 //   k_window_sum     per window: warp-shuffle tree over chunk sums                  [fma pipe]
 //   k_final      Horner over windows (c doublings each) -> ark Jacobian             [latency]
@@ -27,10 +27,10 @@ struct MsmPlan {
   int W;            // number of windows = ceil((scalar_bits + 1) / c)
   uint32_t B;       // buckets per window = 2^(c-1)
   uint32_t NB;      // W * B
-  uint32_t lmax;    // max points per accumulate task
+  uint32_t L;       // sorted entries per accumulate slice (one thread each)
   uint32_t chunk;   // buckets per k_bucket_reduce thread
   uint32_t K;       // chunks per window = B / chunk
-  uint32_t max_tasks;
+  uint32_t max_slots;  // partial slots: slices + buckets
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -191,47 +191,58 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// tasks
-// ---------------------------------------------------------------------------------------------
-static __global__ void k_tasks(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_offsets, uint32_t NB,
-                        uint32_t lmax, uint2* __restrict__ tasks) {
-  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < NB; g += gridDim.x * blockDim.x) {
-    const uint32_t start = offsets[g], cnt = offsets[g + 1] - start;
-    const uint32_t t0 = task_offsets[g];
-    for (uint32_t done = 0, t = t0; done < cnt; done += lmax, t++) {
-      tasks[t] = make_uint2(start + done, min(lmax, cnt - done));
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // bucket accumulation (dominant kernel)
+//
+// The sorted index array (E = offsets[NB] entries, grouped by bucket) is cut into fixed-length
+// slices of L entries; one thread owns one slice, so every lane of a warp performs the same
+// number of mixed additions (no trip-count divergence whatever the bucket-size distribution).
+// A thread walks its slice, and whenever the bucket changes it flushes the accumulator to
+// partials[g + t] (g = bucket id, t = slice id).  Along the (slice, bucket) runs both t and g are
+// non-decreasing and one of them increases, so g + t is a collision-free slot; the reduce kernel
+// finds the runs of bucket g at slices offsets[g]/L .. (offsets[g+1]-1)/L without any task list.
 // ---------------------------------------------------------------------------------------------
 template <class F>
 __global__ void __launch_bounds__(128)
-k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint2* __restrict__ tasks,
-             const uint32_t* __restrict__ num_tasks_ptr, uint32_t* __restrict__ work_counter,
-             uint32_t* __restrict__ partials) {
+k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+             uint32_t NB, uint32_t L, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials) {
   constexpr int AFF = 2 * F::N;
   constexpr int XY = 4 * F::N;
-  const uint32_t NT = *num_tasks_ptr;
+  const uint32_t E = offsets[NB];
+  const uint32_t nslices = (E + L - 1) / L;
   const int lane = threadIdx.x & 31;
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(work_counter, 32u);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= NT) break;
+    if (base >= nslices) break;
     const uint32_t t = base + lane;
-    if (t < NT) {
-      const uint2 tk = tasks[t];
-      XYZZ<F> acc = XYZZ<F>::identity();
-      for (uint32_t k = 0; k < tk.y; k++) {
-        const uint32_t e = sorted[tk.x + k];
-        Affine<F> p = load_affine<F>(bases + (size_t)(e & 0x7fffffffu) * AFF);
-        p.y = p.y.cneg((e >> 31) != 0);
-        acc.add_mixed(p);
+    if (t < nslices) {
+      const uint32_t pos = t * L;
+      const uint32_t end = min(pos + L, E);
+      // bucket containing pos: largest g with offsets[g] <= pos (upper_bound - 1 skips empty buckets)
+      uint32_t lo = 0, hi = NB;  // invariant: offsets[lo] <= pos < offsets[hi]
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= pos) lo = mid; else hi = mid;
       }
-      acc.store(partials + (size_t)t * XY);
+      uint32_t g = lo;
+      uint32_t boundary = offsets[g + 1];
+      XYZZ<F> acc = XYZZ<F>::identity();
+      for (uint32_t p = pos; p < end; p++) {
+        if (p == boundary) {
+          acc.store(partials + (size_t)(g + t) * XY);
+          acc = XYZZ<F>::identity();
+          do {
+            g++;
+            boundary = offsets[g + 1];
+          } while (boundary == p);
+        }
+        const uint32_t e = sorted[p];
+        Affine<F> pt = load_affine<F>(bases + (size_t)(e & 0x7fffffffu) * AFF);
+        pt.y = pt.y.cneg((e >> 31) != 0);
+        acc.add_mixed(pt);
+      }
+      acc.store(partials + (size_t)(g + t) * XY);
     }
   }
 }
@@ -240,10 +251,11 @@ k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ so
 // bucket reduction: for a chunk of buckets [lo, lo + chunk) of window w computes
 //   sum_b (b + 1) * B_b   =   sum_b (b - lo + 1) B_b  +  lo * sum_b B_b
 // by the running-sum recurrence (2 additions per bucket) plus one small scalar multiple.
+// B_b itself is the sum of the bucket's slice partials (see k_accumulate).
 // ---------------------------------------------------------------------------------------------
 template <class F>
 __global__ void __launch_bounds__(128)
-k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restrict__ task_offsets, uint32_t total_chunks,
+k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t L, uint32_t total_chunks,
                 uint32_t K, uint32_t B, uint32_t chunk, uint32_t* __restrict__ chunk_out) {
   constexpr int XY = 4 * F::N;
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,10 +266,13 @@ k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restric
   XYZZ<F> acc = XYZZ<F>::identity();
   for (uint32_t j = chunk; j-- > 0;) {
     const uint32_t g = w * B + lo + j;
-    const uint32_t t0 = task_offsets[g], t1 = task_offsets[g + 1];
-    for (uint32_t t = t0; t < t1; t++) {
-      XYZZ<F> p = XYZZ<F>::load(partials + (size_t)t * XY);
-      running.add(p);
+    const uint32_t o0 = offsets[g], o1 = offsets[g + 1];
+    if (o1 > o0) {
+      const uint32_t t0 = o0 / L, t1 = (o1 - 1) / L;
+      for (uint32_t t = t0; t <= t1; t++) {
+        XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + t) * XY);
+        running.add(p);
+      }
     }
     acc.add(running);
   }

@@ -56,7 +56,7 @@ struct ozl_ctx {
   std::vector<Stage> stages;
   std::vector<Stage> event_pool;
   // workspace
-  DevBuf scalars, counts, offsets, task_offsets, tile_sums, sorted, tasks, partials, chunk_out, window_out, misc, out;
+  DevBuf scalars, counts, offsets, tile_sums, sorted, partials, chunk_out, window_out, misc, out;
   NttWorkspace ntt_ws;
 };
 
@@ -162,14 +162,21 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c) {
   p.W = (lambda + 1 + p.c - 1) / p.c;
   p.B = 1u << (p.c - 1);
   p.NB = (uint32_t)p.W * p.B;
-  p.lmax = 256;
+  // slice length: 128 entries per thread when there is enough work to fill the chip, shorter otherwise
+  {
+    const uint64_t E = (uint64_t)n * p.W;
+    uint64_t L = E / ((uint64_t)148 * 384);
+    if (L > 128) L = 128;
+    if (L < 8) L = 8;
+    p.L = (uint32_t)L;
+  }
   uint32_t chunk = p.B / 1024;
   if (chunk < 4) chunk = 4;
   if (chunk > 64) chunk = 64;
   if (chunk > p.B) chunk = p.B;
   p.chunk = chunk;
   p.K = p.B / chunk;
-  p.max_tasks = p.NB + (uint32_t)(((uint64_t)n * p.W) / p.lmax) + 1;
+  p.max_slots = p.NB + (uint32_t)(((uint64_t)n * p.W) / p.L) + 2;
   return p;
 }
 
@@ -199,19 +206,15 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   int r;
   if ((r = ensure(ctx, ctx->counts, (size_t)p.NB * 4))) return r;
   if ((r = ensure(ctx, ctx->offsets, ((size_t)p.NB + 1) * 4))) return r;
-  if ((r = ensure(ctx, ctx->task_offsets, ((size_t)p.NB + 1) * 4))) return r;
   if ((r = ensure(ctx, ctx->sorted, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
-  if ((r = ensure(ctx, ctx->tasks, (size_t)p.max_tasks * 8))) return r;
-  if ((r = ensure(ctx, ctx->partials, (size_t)p.max_tasks * XY * 4))) return r;
+  if ((r = ensure(ctx, ctx->partials, (size_t)p.max_slots * XY * 4))) return r;
   if ((r = ensure(ctx, ctx->chunk_out, (size_t)p.W * p.K * XY * 4))) return r;
   if ((r = ensure(ctx, ctx->window_out, (size_t)p.W * XY * 4))) return r;
   if ((r = ensure(ctx, ctx->misc, 64))) return r;
 
   uint32_t* counts = (uint32_t*)ctx->counts.p;
   uint32_t* offsets = (uint32_t*)ctx->offsets.p;
-  uint32_t* task_offsets = (uint32_t*)ctx->task_offsets.p;
   uint32_t* sorted = (uint32_t*)ctx->sorted.p;
-  uint2* tasks = (uint2*)ctx->tasks.p;
   uint32_t* partials = (uint32_t*)ctx->partials.p;
   uint32_t* chunk_out = (uint32_t*)ctx->chunk_out.p;
   uint32_t* window_out = (uint32_t*)ctx->window_out.p;
@@ -228,24 +231,21 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
 
   STAGE(ctx, "scan");
   if ((r = run_scan(ctx, counts, p.NB, offsets, ScanIdentity{1}))) return r;
-  if ((r = run_scan(ctx, counts, p.NB, task_offsets, ScanCeilDiv{p.lmax}))) return r;
   STAGE_END(ctx);
 
   STAGE(ctx, "scatter");
   k_scatter<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.B, offsets, counts, sorted);
   LAUNCH_CHECK(ctx);
-  k_tasks<<<grid_io, 256, 0, st>>>(offsets, task_offsets, p.NB, p.lmax, tasks);
-  LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
   STAGE(ctx, "accumulate");
-  k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, tasks, task_offsets + p.NB, work_counter, partials);
+  k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, p.L, work_counter, partials);
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
   STAGE(ctx, "bucket_reduce");
   const uint32_t total_chunks = (uint32_t)p.W * p.K;
-  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, task_offsets, total_chunks, p.K, p.B, p.chunk, chunk_out);
+  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, offsets, p.L, total_chunks, p.K, p.B, p.chunk, chunk_out);
   LAUNCH_CHECK(ctx);
   k_window_sum<F><<<p.W, 256, 0, st>>>(chunk_out, p.K, window_out);
   LAUNCH_CHECK(ctx);
