@@ -96,7 +96,7 @@ void ozl_ctx_destroy(ozl_ctx* ctx) {
     cudaFree(kv.second.d_pts);
     if (kv.second.d_inf) cudaFree(kv.second.d_inf);
   }
-  DevBuf* bufs[] = {&ctx->scalars, &ctx->counts, &ctx->offsets, &ctx->tile_sums, &ctx->sorted,
+  DevBuf* bufs[] = {&ctx->scalars, &ctx->counts, &ctx->offsets, &ctx->tile_sums, &ctx->sorted, &ctx->digits,
                     &ctx->partials, &ctx->chunk_out, &ctx->window_out, &ctx->misc, &ctx->out};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);

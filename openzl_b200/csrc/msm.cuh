@@ -7,7 +7,7 @@
 //
 //   k_count      scalars -> signed c-bit digits, histogram of (window, bucket)       [HBM/L2 atomics]
 //   scan         bucket offsets                                                     [HBM]
-//   k_scatter    counting-sort point indices by (window, bucket)                    [HBM/L2 atomics]
+//   k_scatter_window  counting-sort point indices by bucket, one launch per window   [HBM/L2 atomics]
 //   k_accumulate one thread per fixed-length slice of the sorted indices: gather
 //                affine points, XYZZ mixed adds, flush at bucket boundaries         [fma pipe]  <- dominant
 //   k_bucket_reduce  per chunk of buckets: running sum  sum (b+1) B_b               [fma pipe]
@@ -36,57 +36,54 @@ struct MsmPlan {
 // ---------------------------------------------------------------------------------------------
 // digits
 // ---------------------------------------------------------------------------------------------
-// Calls f(window, bucket, negative) for every non-zero signed digit of the 256-bit scalar s.
-template <class Fn>
-__device__ __forceinline__ void for_each_digit(const uint32_t* __restrict__ s, int c, int W, Fn f) {
-  uint32_t carry = 0;
-  const uint32_t mask = (1u << c) - 1u;
-  const uint32_t half = 1u << (c - 1);
-  for (int w = 0; w < W; w++) {
-    const int bit = w * c;
-    const int limb = bit >> 5, off = bit & 31;
-    uint64_t lo = 0;
-    if (limb < 8) lo = s[limb];
-    if (limb + 1 < 8) lo |= (uint64_t)s[limb + 1] << 32;
-    uint32_t v = ((uint32_t)(lo >> off) & mask) + carry;
-    uint32_t neg = 0;
-    carry = 0;
-    if (v > half) {
-      v = (1u << c) - v;
-      neg = 1;
-      carry = 1;
-    }
-    if (v) f(w, v - 1, neg);
-  }
-}
-
+// Digit extraction + histogram.  Writes the signed digit of every (window, scalar) pair to the
+// window-major array digits[w * n + i] (encoded bucket+1, sign in bit 31, 0 = no contribution) so
+// that the scatter can run window by window over contiguous 4-byte entries.
 static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t n,
-                        int c, int W, uint32_t B, uint32_t* __restrict__ counts) {
+                               int c, int W, uint32_t B, uint32_t* __restrict__ counts, uint32_t* __restrict__ digits) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (inf_mask && ((inf_mask[i >> 3] >> (i & 7)) & 1)) continue;
+    const bool skip = inf_mask && ((inf_mask[i >> 3] >> (i & 7)) & 1);
     uint32_t s[8];
     const uint4* sp = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
     uint4 a = sp[0], b = sp[1];
     s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
-    for_each_digit(s, c, W, [&](int w, uint32_t bucket, uint32_t) { atomicAdd(&counts[(uint32_t)w * B + bucket], 1u); });
+    uint32_t carry = 0;
+    const uint32_t mask = (1u << c) - 1u;
+    const uint32_t half = 1u << (c - 1);
+    for (int w = 0; w < W; w++) {
+      const int bit = w * c;
+      const int limb = bit >> 5, off = bit & 31;
+      uint64_t lo = 0;
+      if (limb < 8) lo = s[limb];
+      if (limb + 1 < 8) lo |= (uint64_t)s[limb + 1] << 32;
+      uint32_t v = ((uint32_t)(lo >> off) & mask) + carry;
+      uint32_t neg = 0;
+      carry = 0;
+      if (v > half) {
+        v = (1u << c) - v;
+        neg = 1;
+        carry = 1;
+      }
+      if (skip) v = 0;
+      digits[(size_t)w * n + i] = v ? (v | (neg << 31)) : 0u;
+      if (v) atomicAdd(&counts[(uint32_t)w * B + (v - 1)], 1u);
+    }
   }
 }
 
-static __global__ void k_scatter(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t n,
-                          int c, int W, uint32_t B, const uint32_t* __restrict__ offsets,
-                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+// Counting-sort scatter of ONE window: the window's cursors (2^(c-1) words), offsets and the
+// 32-byte sectors being filled all stay L2-resident, so each sector of `sorted` reaches HBM once.
+static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, uint32_t n, uint32_t g_base,
+                                        const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
+                                        uint32_t* __restrict__ sorted) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (inf_mask && ((inf_mask[i >> 3] >> (i & 7)) & 1)) continue;
-    uint32_t s[8];
-    const uint4* sp = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
-    uint4 a = sp[0], b = sp[1];
-    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
-    for_each_digit(s, c, W, [&](int w, uint32_t bucket, uint32_t neg) {
-      const uint32_t g = (uint32_t)w * B + bucket;
+    const uint32_t d = digits_w[i];
+    if (d) {
+      const uint32_t g = g_base + (d & 0x7fffffffu) - 1u;
       // cursor[] enters holding the bucket's count; filling from the back leaves it zeroed
       const uint32_t pos = atomicSub(&cursor[g], 1u) - 1u;
-      sorted[offsets[g] + pos] = i | (neg << 31);
-    });
+      sorted[offsets[g] + pos] = i | (d & 0x80000000u);
+    }
   }
 }
 

@@ -56,7 +56,7 @@ struct ozl_ctx {
   std::vector<Stage> stages;
   std::vector<Stage> event_pool;
   // workspace
-  DevBuf scalars, counts, offsets, tile_sums, sorted, partials, chunk_out, window_out, misc, out;
+  DevBuf scalars, counts, offsets, tile_sums, sorted, digits, partials, chunk_out, window_out, misc, out;
   NttWorkspace ntt_ws;
 };
 
@@ -170,9 +170,9 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c) {
     if (L < 8) L = 8;
     p.L = (uint32_t)L;
   }
-  uint32_t chunk = p.B / 1024;
+  uint32_t chunk = p.B / 4096;
   if (chunk < 4) chunk = 4;
-  if (chunk > 64) chunk = 64;
+  if (chunk > 16) chunk = 16;
   if (chunk > p.B) chunk = p.B;
   p.chunk = chunk;
   p.K = p.B / chunk;
@@ -207,6 +207,7 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   if ((r = ensure(ctx, ctx->counts, (size_t)p.NB * 4))) return r;
   if ((r = ensure(ctx, ctx->offsets, ((size_t)p.NB + 1) * 4))) return r;
   if ((r = ensure(ctx, ctx->sorted, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
+  if ((r = ensure(ctx, ctx->digits, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
   if ((r = ensure(ctx, ctx->partials, (size_t)p.max_slots * XY * 4))) return r;
   if ((r = ensure(ctx, ctx->chunk_out, (size_t)p.W * p.K * XY * 4))) return r;
   if ((r = ensure(ctx, ctx->window_out, (size_t)p.W * XY * 4))) return r;
@@ -215,6 +216,7 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   uint32_t* counts = (uint32_t*)ctx->counts.p;
   uint32_t* offsets = (uint32_t*)ctx->offsets.p;
   uint32_t* sorted = (uint32_t*)ctx->sorted.p;
+  uint32_t* digits = (uint32_t*)ctx->digits.p;
   uint32_t* partials = (uint32_t*)ctx->partials.p;
   uint32_t* chunk_out = (uint32_t*)ctx->chunk_out.p;
   uint32_t* window_out = (uint32_t*)ctx->window_out.p;
@@ -225,7 +227,7 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   STAGE(ctx, "digits_count");
   CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)p.NB * 4, st));
   CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 64, st));
-  k_count<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.B, counts);
+  k_count<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.B, counts, digits);
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
@@ -234,8 +236,10 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   STAGE_END(ctx);
 
   STAGE(ctx, "scatter");
-  k_scatter<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.B, offsets, counts, sorted);
-  LAUNCH_CHECK(ctx);
+  for (int w = 0; w < p.W && n; w++) {
+    k_scatter_window<<<grid_io, 256, 0, st>>>(digits + (size_t)w * n, (uint32_t)n, (uint32_t)w * p.B, offsets, counts, sorted);
+    LAUNCH_CHECK(ctx);
+  }
   STAGE_END(ctx);
 
   STAGE(ctx, "accumulate");
