@@ -40,13 +40,13 @@ struct XYZZ {
   static OZL_DEV_NOINLINE XYZZ dbl_affine(const Affine<F>& p) {
     XYZZ r;
     F u = p.y.dbl();
-    F v = u.sqr();
-    F w = u * v;
-    F s = p.x * v;
-    F xx = p.x.sqr();
+    F v = F::sqr_ni(u);
+    F w = F::mul_ni(u, v);
+    F s = F::mul_ni(p.x, v);
+    F xx = F::sqr_ni(p.x);
     F m = xx.dbl() + xx;
-    r.x = m.sqr() - s.dbl();
-    r.y = m * (s - r.x) - w * p.y;
+    r.x = F::sqr_ni(m) - s.dbl();
+    r.y = F::mul_ni(m, s - r.x) - F::mul_ni(w, p.y);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -57,15 +57,15 @@ struct XYZZ {
     if (is_identity()) return *this;
     XYZZ r;
     F u = y.dbl();
-    F v = u.sqr();
-    F w = u * v;
-    F s = x * v;
-    F xx = x.sqr();
+    F v = F::sqr_ni(u);
+    F w = F::mul_ni(u, v);
+    F s = F::mul_ni(x, v);
+    F xx = F::sqr_ni(x);
     F m = xx.dbl() + xx;
-    r.x = m.sqr() - s.dbl();
-    r.y = m * (s - r.x) - w * y;
-    r.zz = v * zz;
-    r.zzz = w * zzz;
+    r.x = F::sqr_ni(m) - s.dbl();
+    r.y = F::mul_ni(m, s - r.x) - F::mul_ni(w, y);
+    r.zz = F::mul_ni(v, zz);
+    r.zzz = F::mul_ni(w, zzz);
     return r;
   }
 
@@ -98,7 +98,32 @@ struct XYZZ {
   }
 
   // out-of-line copy of add_mixed for cold kernels (keeps their code size small)
-  OZL_DEV_NOINLINE void add_mixed_cold(const Affine<F>& p) { add_mixed(p); }
+  OZL_DEV_NOINLINE void add_mixed_cold(const Affine<F>& p) {
+    if (is_identity()) {
+      *this = from_affine(p);
+      return;
+    }
+    F u2 = F::mul_ni(p.x, zz);
+    F s2 = F::mul_ni(p.y, zzz);
+    F pp = u2 - x;
+    F r = s2 - y;
+    if (pp.is_zero()) {
+      if (r.is_zero()) {
+        *this = dbl_affine(p);
+      } else {
+        *this = identity();
+      }
+      return;
+    }
+    F p2 = F::sqr_ni(pp);
+    F p3 = F::mul_ni(pp, p2);
+    F q = F::mul_ni(x, p2);
+    F x3 = F::sqr_ni(r) - p3 - q.dbl();
+    y = F::mul_ni(r, q - x3) - F::mul_ni(y, p3);
+    x = x3;
+    zz = F::mul_ni(zz, p2);
+    zzz = F::mul_ni(zzz, p3);
+  }
 
   // this += o (add-2008-s)
   OZL_DEV_NOINLINE void add(const XYZZ& o) {
@@ -107,10 +132,10 @@ struct XYZZ {
       *this = o;
       return;
     }
-    F u1 = x * o.zz;
-    F u2 = o.x * zz;
-    F s1 = y * o.zzz;
-    F s2 = o.y * zzz;
+    F u1 = F::mul_ni(x, o.zz);
+    F u2 = F::mul_ni(o.x, zz);
+    F s1 = F::mul_ni(y, o.zzz);
+    F s2 = F::mul_ni(o.y, zzz);
     F pp = u2 - u1;
     F r = s2 - s1;
     if (pp.is_zero()) {
@@ -121,14 +146,14 @@ struct XYZZ {
       }
       return;
     }
-    F p2 = pp.sqr();
-    F p3 = pp * p2;
-    F q = u1 * p2;
-    F x3 = r.sqr() - p3 - q.dbl();
-    y = r * (q - x3) - s1 * p3;
+    F p2 = F::sqr_ni(pp);
+    F p3 = F::mul_ni(pp, p2);
+    F q = F::mul_ni(u1, p2);
+    F x3 = F::sqr_ni(r) - p3 - q.dbl();
+    y = F::mul_ni(r, q - x3) - F::mul_ni(s1, p3);
     x = x3;
-    zz = zz * o.zz * p2;
-    zzz = zzz * o.zzz * p3;
+    zz = F::mul_ni(F::mul_ni(zz, o.zz), p2);
+    zzz = F::mul_ni(F::mul_ni(zzz, o.zzz), p3);
   }
 
   // [k] * this for a small unsigned k (left-to-right double-and-add); cold path.
@@ -155,10 +180,10 @@ struct XYZZ {
   // affine (x, y); returns false for the identity
   OZL_DEV_NOINLINE bool to_affine(Affine<F>& p) const {
     if (is_identity()) return false;
-    F zi = zzz.inverse();          // 1/Z^3
-    F zi2 = (zi * zz).sqr();       // (1/Z)^2 = (ZZ/ZZZ)^2
-    p.x = x * zi2;
-    p.y = y * zi;
+    F zi = zzz.inverse();                      // 1/Z^3
+    F zi2 = F::sqr_ni(F::mul_ni(zi, zz));      // (1/Z)^2 = (ZZ/ZZZ)^2
+    p.x = F::mul_ni(x, zi2);
+    p.y = F::mul_ni(y, zi);
     return true;
   }
 
