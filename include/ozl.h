@@ -125,6 +125,54 @@ int ozl_ntt(ozl_ctx* ctx, int field, uint64_t* data, uint32_t log_n, int inverse
 int ozl_ntt_device_async(ozl_ctx* ctx, int field, uint64_t* d_data, uint32_t log_n, int inverse,
                          int coset);
 
+/* ---- Groth16 prover: replaces ark_groth16::create_proof behind groth16.rs:454 -------------- */
+/* Pairing-friendly curve families (`Pairing`, /root/reference/plugins/arkworks/src/pairing.rs:9-38). */
+typedef enum {
+  OZL_PAIRING_BN254 = 0,
+  OZL_PAIRING_BLS12_381 = 1
+} ozl_pairing;
+
+/* One R1CS matrix in CSR form.  Coefficients are indices into a shared table of field elements
+ * (Montgomery) because gadget-built systems have very few distinct constants. */
+typedef struct {
+  uint32_t n_rows;
+  const uint32_t* row_ptr;  /* n_rows + 1 */
+  const uint32_t* col_idx;  /* row_ptr[n_rows] */
+  const uint32_t* coef_idx; /* row_ptr[n_rows] */
+} ozl_csr;
+
+/* y = M x over the pairing's scalar field; x has n_cols elements, y gets M->n_rows (host buffers,
+ * Montgomery).  Used by the setup (transposed matrices) and by tests of the witness map. */
+int ozl_fr_spmv(ozl_ctx* ctx, int field, const ozl_csr* M, const uint64_t* coef_table, uint32_t n_coef,
+                const uint64_t* x, uint32_t n_cols, uint64_t* y);
+
+/* out_affine[j] = [scalars[j]] G for the curve's generator G; identity_flags[j] = 1 for the point
+ * at infinity.  The fixed-base work of a (known-trapdoor) Groth16 setup. */
+int ozl_fixed_base_mul(ozl_ctx* ctx, int curve, const uint64_t* scalars, size_t n, uint64_t* out_affine,
+                       uint8_t* identity_flags);
+
+/* Proving key resident on the device: `ProvingKey{vk.alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2,
+ * a_query, b_g1_query, b_g2_query, h_query, l_query}` (field names as destructured at
+ * groth16.rs:200-205) plus the circuit's A, B, C matrices.  The five query vectors are bases
+ * handles uploaded beforehand (sizes: a/b_g1/b_g2 = n_vars, h = domain - 1, l = n_vars - n_instance);
+ * the pk takes ownership of them.  n_instance counts the leading constant 1. */
+int ozl_groth16_pk_create(ozl_ctx* ctx, int pairing, uint32_t n_constraints, uint32_t n_instance, uint32_t n_vars,
+                          const ozl_csr* A, const ozl_csr* B, const ozl_csr* C, const uint64_t* coef_table,
+                          uint32_t n_coef, uint32_t a_query, uint32_t b_g1_query, uint32_t b_g2_query,
+                          uint32_t h_query, uint32_t l_query, const uint64_t* alpha_g1, const uint64_t* beta_g1,
+                          const uint64_t* delta_g1, const uint64_t* beta_g2, const uint64_t* delta_g2,
+                          uint32_t* pk_handle);
+int ozl_groth16_pk_destroy(ozl_ctx* ctx, uint32_t pk_handle);
+
+/* `create_proof(circuit, pk, r, s)`: z = full assignment (1, instance..., witness...) as n_vars
+ * Montgomery elements; r, s = the two blinding scalars (canonical, drawn by the caller's rng like
+ * `create_random_proof`).  Outputs affine A (G1), B (G2), C (G1).  h_out, if non-NULL, receives the
+ * domain_size quotient coefficients (Montgomery) for inspection. */
+int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                      uint64_t* proof_a, uint64_t* proof_b, uint64_t* proof_c, uint64_t* h_out);
+/* Domain size 2^k = next_pow2(n_constraints + n_instance) of a pk (ark's witness_map sizing). */
+int ozl_groth16_domain_size(ozl_ctx* ctx, uint32_t pk_handle, uint32_t* out);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* When enabled, every pipeline stage of the next calls is bracketed with CUDA events on the
  * context's stream.  ozl_ctx_get_stage_times copies up to `cap` (name, ms, launches) records of

@@ -28,7 +28,8 @@ EXPORTS = [
     "ozl_msm_bases_upload_device", "ozl_msm_bases_generate", "ozl_msm_bases_download", "ozl_msm_bases_free",
     "ozl_msm", "ozl_msm_device_async", "ozl_msm_set_window_bits", "ozl_msm_get_window_bits", "ozl_jacobian_sum",
     "ozl_jacobian_to_affine", "ozl_ntt", "ozl_ntt_device_async", "ozl_ctx_enable_timing",
-    "ozl_ctx_get_stage_times", "ozl_ctx_launch_count", "ozl_bench_field_mul",
+    "ozl_ctx_get_stage_times", "ozl_ctx_launch_count", "ozl_bench_field_mul", "ozl_fr_spmv", "ozl_fixed_base_mul",
+    "ozl_groth16_pk_create", "ozl_groth16_pk_destroy", "ozl_groth16_prove", "ozl_groth16_domain_size",
 ]
 
 
@@ -43,6 +44,11 @@ class OzlError(RuntimeError):
     def __init__(self, status: int, where: str, detail: str = ""):
         self.status = status
         super().__init__(f"{where}: {STATUS_NAMES.get(status, status)}" + (f" ({detail})" if detail else ""))
+
+
+class Csr(ctypes.Structure):
+    _fields_ = [("n_rows", ctypes.c_uint32), ("row_ptr", ctypes.c_void_p), ("col_idx", ctypes.c_void_p),
+                ("coef_idx", ctypes.c_void_p)]
 
 
 class StageTime(ctypes.Structure):
@@ -96,5 +102,14 @@ def load() -> ctypes.CDLL:
     lib.ozl_ctx_launch_count.argtypes = [vp]
     lib.ozl_ctx_launch_count.restype = ctypes.c_uint64
     lib.ozl_bench_field_mul.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    csrp = ctypes.POINTER(Csr)
+    u32 = ctypes.c_uint32
+    lib.ozl_fr_spmv.argtypes = [vp, ctypes.c_int, csrp, vp, u32, vp, u32, vp]
+    lib.ozl_fixed_base_mul.argtypes = [vp, ctypes.c_int, vp, sz, vp, vp]
+    lib.ozl_groth16_pk_create.argtypes = [vp, ctypes.c_int, u32, u32, u32, csrp, csrp, csrp, vp, u32, u32, u32, u32, u32, u32,
+                                          vp, vp, vp, vp, vp, u32p]
+    lib.ozl_groth16_pk_destroy.argtypes = [vp, u32]
+    lib.ozl_groth16_prove.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp]
+    lib.ozl_groth16_domain_size.argtypes = [vp, u32, u32p]
     _lib = lib
     return lib

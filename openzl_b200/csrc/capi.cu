@@ -100,7 +100,8 @@ void ozl_ctx_destroy(ozl_ctx* ctx) {
                     &ctx->partials, &ctx->chunk_out, &ctx->window_out, &ctx->misc, &ctx->out};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
-  void* nb[] = {ctx->ntt_ws.scratch, ctx->ntt_ws.tw, ctx->ntt_ws.glo, ctx->ntt_ws.ghi, ctx->ntt_ws.consts};
+  NttWorkspace& nw = ctx->ntt_ws;
+  void* nb[] = {nw.scratch, nw.tw[0], nw.tw[1], nw.glo[0], nw.glo[1], nw.ghi[0], nw.ghi[1], nw.consts[0], nw.consts[1]};
   for (void* p : nb)
     if (p) cudaFree(p);
   cudaStreamDestroy(ctx->own_stream);

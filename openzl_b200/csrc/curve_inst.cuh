@@ -21,6 +21,15 @@ void jaff_entry(cudaStream_t st, const uint32_t* d_jac, uint32_t* d_out, int* d_
 void bench_entry(cudaStream_t st, int blocks, int threads, uint32_t* d_out, int iters) {
   k_bench_mul<Fp<OZL_BASE>><<<blocks, threads, 0, st>>>(d_out, iters);
 }
+void fixed_base_entry(cudaStream_t st, const uint32_t* d_scalars, uint32_t n, uint32_t* d_out, uint8_t* d_flags) {
+  k_fixed_base_mul<F_, C_><<<(n + 127) / 128, 128, 0, st>>>(d_scalars, n, d_out, d_flags);
+}
+void lincomb_entry(cudaStream_t st, const uint32_t* d_pts, const uint32_t* d_scalars, uint32_t k, uint32_t* d_out) {
+  k_lincomb<F_><<<1, 32, 0, st>>>(d_pts, d_scalars, k, d_out);
+}
+void a2j_entry(cudaStream_t st, const uint32_t* d_aff, uint32_t* d_out) {
+  k_affine_to_jacobian<F_><<<1, 32, 0, st>>>(d_aff, d_out);
+}
 }  // namespace
 
-const OzlCurveOps OZL_OPS = {msm_entry, generate_entry, jsum_entry, jaff_entry, bench_entry};
+const OzlCurveOps OZL_OPS = {msm_entry, generate_entry, jsum_entry, jaff_entry, bench_entry, fixed_base_entry, lincomb_entry, a2j_entry};

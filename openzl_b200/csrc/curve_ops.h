@@ -19,12 +19,29 @@ struct OzlCurveOps {
   void (*jacobian_sum)(cudaStream_t st, const uint32_t* d_pts, uint32_t k, uint32_t* d_out);
   void (*jacobian_to_affine)(cudaStream_t st, const uint32_t* d_jac, uint32_t* d_out, int* d_flag);
   void (*bench_mul)(cudaStream_t st, int blocks, int threads, uint32_t* d_out, int iters);  // base-field multiplier
+  // out_affine[j] = [k_j] G (canonical 256-bit k_j); flags[j] = 1 when the result is the identity
+  void (*fixed_base_mul)(cudaStream_t st, const uint32_t* d_scalars, uint32_t n, uint32_t* d_out_affine, uint8_t* d_flags);
+  // out_jac = sum_{i<k} scalars[i] * pts_jac[i]   (k <= 32; one lane per term)
+  void (*lincomb)(cudaStream_t st, const uint32_t* d_pts_jac, const uint32_t* d_scalars, uint32_t k, uint32_t* d_out_jac);
+  // Jacobian <- affine (x||y) on the device, for constants uploaded from the host
+  void (*affine_to_jacobian)(cudaStream_t st, const uint32_t* d_aff, uint32_t* d_out_jac);
 };
 
 extern const OzlCurveOps ozl_ops_bls12_381_g1;
 extern const OzlCurveOps ozl_ops_bls12_381_g2;
 extern const OzlCurveOps ozl_ops_bn254_g1;
 extern const OzlCurveOps ozl_ops_bn254_g2;
+
+struct OzlFieldOps {
+  int (*ntt)(cudaStream_t st, ozl::NttWorkspace& ws, uint32_t* d_data, uint32_t log_n, bool inverse, bool coset, int* launches);
+  void (*spmv)(cudaStream_t st, const uint32_t* row_ptr, const uint32_t* col, const uint32_t* cidx, const uint32_t* coef,
+               const uint32_t* x, uint32_t n_rows, uint32_t* y);
+  void (*from_mont)(cudaStream_t st, const uint32_t* in, uint32_t* out, uint32_t n);
+  void (*h_pointwise)(cudaStream_t st, uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* scale, uint32_t n);
+  void (*vanishing_inv)(cudaStream_t st, int log_n, uint32_t* out);
+};
+extern const OzlFieldOps ozl_fops_bn254_fr;
+extern const OzlFieldOps ozl_fops_bls12_381_fr;
 
 int ozl_ntt_run_bn254_fr(cudaStream_t st, ozl::NttWorkspace& ws, uint32_t* d_data, uint32_t log_n, bool inverse, bool coset, int* launches);
 int ozl_ntt_run_bls12_381_fr(cudaStream_t st, ozl::NttWorkspace& ws, uint32_t* d_data, uint32_t log_n, bool inverse, bool coset, int* launches);

@@ -1,0 +1,356 @@
+// Groth16 prover orchestration on the device: the restatement of ark_groth16::create_proof /
+// R1CStoQAP::witness_map (ark-groth16 0.3.0) that plugins/arkworks reaches at
+// /root/reference/plugins/arkworks/src/groth16.rs:454, with the step order of SURVEY.md section 3.1:
+//   a = A z, b = B z, c = C z (instance rows appended to a) -> ifft x3 -> coset_fft x3 ->
+//   h = (a*b - c) / Z(g) -> coset_ifft -> MSM(h_query, h) ; MSM(l_query, aux) ; MSM(a_query, z) ;
+//   MSM(b_g1_query, z) ; MSM(b_g2_query, z) -> A = alpha + a_acc + r delta, B = beta + b_acc + s delta,
+//   C = l_acc + h_acc + s A + r B1 - r s delta  (computed as l + h + s A + r (beta1 + b1_acc)).
+// Everything between the H2D copy of z and the D2H copy of the three proof points stays in HBM.
+#include "runtime.cuh"
+
+namespace {
+
+struct DevCsr {
+  uint32_t n_rows = 0;
+  uint32_t* row_ptr = nullptr;
+  uint32_t* col = nullptr;
+  uint32_t* cidx = nullptr;
+};
+
+struct Groth16Pk {
+  int pairing = 0;
+  uint32_t n_constraints = 0, n_instance = 0, n_vars = 0, log_n = 0;
+  DevCsr A, B, C;
+  uint32_t* coef = nullptr;
+  uint32_t h_a = 0, h_b1 = 0, h_b2 = 0, h_h = 0, h_l = 0;
+  uint32_t* consts_g1 = nullptr;  // Jacobian alpha1, beta1, delta1
+  uint32_t* consts_g2 = nullptr;  // Jacobian beta2, delta2
+  uint32_t* zinv = nullptr;       // 1/(g^n - 1)
+  // per-proof workspace
+  uint32_t *z = nullptr, *zc = nullptr, *a = nullptr, *b = nullptr, *c = nullptr, *hc = nullptr;
+  uint32_t *acc = nullptr;        // MSM outputs + assembly scratch
+  uint32_t *rs = nullptr;         // scalars for the assembly
+};
+
+std::map<uint32_t, Groth16Pk>& pk_registry() {
+  static std::map<uint32_t, Groth16Pk> r;
+  return r;
+}
+uint32_t g_next_pk = 1;
+
+void free_csr(DevCsr& m) {
+  if (m.row_ptr) cudaFree(m.row_ptr);
+  if (m.col) cudaFree(m.col);
+  if (m.cidx) cudaFree(m.cidx);
+  m = DevCsr();
+}
+
+int upload_csr(ozl_ctx* ctx, const ozl_csr* h, DevCsr* d) {
+  d->n_rows = h->n_rows;
+  const size_t nnz = h->row_ptr[h->n_rows];
+  CUDA_TRY(ctx, cudaMalloc((void**)&d->row_ptr, ((size_t)h->n_rows + 1) * 4));
+  CUDA_TRY(ctx, cudaMalloc((void**)&d->col, std::max<size_t>(nnz, 1) * 4));
+  CUDA_TRY(ctx, cudaMalloc((void**)&d->cidx, std::max<size_t>(nnz, 1) * 4));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d->row_ptr, h->row_ptr, ((size_t)h->n_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d->col, h->col_idx, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d->cidx, h->coef_idx, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return OZL_OK;
+}
+
+const OzlFieldOps* field_ops(int field) {
+  if (field == OZL_BN254_FR) return &ozl_fops_bn254_fr;
+  if (field == OZL_BLS12_381_FR) return &ozl_fops_bls12_381_fr;
+  return nullptr;
+}
+const OzlCurveOps* g1_ops(int pairing) { return pairing == OZL_PAIRING_BN254 ? &ozl_ops_bn254_g1 : &ozl_ops_bls12_381_g1; }
+const OzlCurveOps* g2_ops(int pairing) { return pairing == OZL_PAIRING_BN254 ? &ozl_ops_bn254_g2 : &ozl_ops_bls12_381_g2; }
+int g1_curve(int pairing) { return pairing == OZL_PAIRING_BN254 ? OZL_BN254_G1 : OZL_BLS12_381_G1; }
+int g2_curve(int pairing) { return pairing == OZL_PAIRING_BN254 ? OZL_BN254_G2 : OZL_BLS12_381_G2; }
+int fr_field(int pairing) { return pairing == OZL_PAIRING_BN254 ? OZL_BN254_FR : OZL_BLS12_381_FR; }
+
+void destroy_pk(ozl_ctx* ctx, Groth16Pk& pk) {
+  cudaStreamSynchronize(ctx->stream);
+  free_csr(pk.A); free_csr(pk.B); free_csr(pk.C);
+  void* ptrs[] = {pk.coef, pk.consts_g1, pk.consts_g2, pk.zinv, pk.z, pk.zc, pk.a, pk.b, pk.c, pk.hc, pk.acc, pk.rs};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (uint32_t h : {pk.h_a, pk.h_b1, pk.h_b2, pk.h_h, pk.h_l}) ozl_msm_bases_free(ctx, h);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ozl_fr_spmv(ozl_ctx* ctx, int field, const ozl_csr* M, const uint64_t* coef_table, uint32_t n_coef,
+                const uint64_t* x, uint32_t n_cols, uint64_t* y) {
+  if (!ctx || !M || !M->row_ptr || !coef_table || !x || !y) return OZL_ERR_ARG;
+  const OzlFieldOps* f = field_ops(field);
+  if (!f) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  DevCsr d;
+  int r = upload_csr(ctx, M, &d);
+  uint32_t *dc = nullptr, *dx = nullptr, *dy = nullptr;
+  auto cleanup = [&]() { free_csr(d); if (dc) cudaFree(dc); if (dx) cudaFree(dx); if (dy) cudaFree(dy); };
+  if (r) { cleanup(); return r; }
+  if (cudaMalloc((void**)&dc, std::max<size_t>(n_coef, 1) * 32) != cudaSuccess ||
+      cudaMalloc((void**)&dx, std::max<size_t>(n_cols, 1) * 32) != cudaSuccess ||
+      cudaMalloc((void**)&dy, std::max<size_t>(M->n_rows, 1) * 32) != cudaSuccess) { cleanup(); return OZL_ERR_OOM; }
+  cudaMemcpyAsync(dc, coef_table, (size_t)n_coef * 32, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dx, x, (size_t)n_cols * 32, cudaMemcpyHostToDevice, ctx->stream);
+  f->spmv(ctx->stream, d.row_ptr, d.col, d.cidx, dc, dx, M->n_rows, dy);
+  ctx->launches++;
+  cudaMemcpyAsync(y, dy, (size_t)M->n_rows * 32, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (e != cudaSuccess) { ctx->last_error = std::string("fr_spmv: ") + cudaGetErrorString(e); return OZL_ERR_CUDA; }
+  return OZL_OK;
+}
+
+int ozl_fixed_base_mul(ozl_ctx* ctx, int curve, const uint64_t* scalars, size_t n, uint64_t* out_affine,
+                       uint8_t* identity_flags) {
+  if (!ctx || (!scalars && n) || !out_affine || !identity_flags || !coord_u32(curve) || n >= 0x7fffffffull) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const OzlCurveOps* ops = nullptr;
+  switch (curve) {
+    case OZL_BLS12_381_G1: ops = &ozl_ops_bls12_381_g1; break;
+    case OZL_BLS12_381_G2: ops = &ozl_ops_bls12_381_g2; break;
+    case OZL_BN254_G1: ops = &ozl_ops_bn254_g1; break;
+    case OZL_BN254_G2: ops = &ozl_ops_bn254_g2; break;
+  }
+  if (!n) return OZL_OK;
+  const size_t aff_bytes = 2 * (size_t)coord_u32(curve) * 4;
+  uint32_t *ds = nullptr, *dout = nullptr;
+  uint8_t* dfl = nullptr;
+  auto cleanup = [&]() { if (ds) cudaFree(ds); if (dout) cudaFree(dout); if (dfl) cudaFree(dfl); };
+  if (cudaMalloc((void**)&ds, n * 32) != cudaSuccess || cudaMalloc((void**)&dout, n * aff_bytes) != cudaSuccess ||
+      cudaMalloc((void**)&dfl, n) != cudaSuccess) { cleanup(); return OZL_ERR_OOM; }
+  cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+  ops->fixed_base_mul(ctx->stream, ds, (uint32_t)n, dout, dfl);
+  ctx->launches++;
+  cudaMemcpyAsync(out_affine, dout, n * aff_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaMemcpyAsync(identity_flags, dfl, n, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (e != cudaSuccess) { ctx->last_error = std::string("fixed_base_mul: ") + cudaGetErrorString(e); return OZL_ERR_CUDA; }
+  return OZL_OK;
+}
+
+int ozl_groth16_pk_create(ozl_ctx* ctx, int pairing, uint32_t n_constraints, uint32_t n_instance, uint32_t n_vars,
+                          const ozl_csr* A, const ozl_csr* B, const ozl_csr* C, const uint64_t* coef_table,
+                          uint32_t n_coef, uint32_t a_query, uint32_t b_g1_query, uint32_t b_g2_query,
+                          uint32_t h_query, uint32_t l_query, const uint64_t* alpha_g1, const uint64_t* beta_g1,
+                          const uint64_t* delta_g1, const uint64_t* beta_g2, const uint64_t* delta_g2,
+                          uint32_t* pk_handle) {
+  if (!ctx || !A || !B || !C || !coef_table || !alpha_g1 || !beta_g1 || !delta_g1 || !beta_g2 || !delta_g2 || !pk_handle)
+    return OZL_ERR_ARG;
+  if (pairing != OZL_PAIRING_BN254 && pairing != OZL_PAIRING_BLS12_381) return OZL_ERR_ARG;
+  if (A->n_rows != n_constraints || B->n_rows != n_constraints || C->n_rows != n_constraints) return OZL_ERR_ARG;
+  if (n_instance == 0 || n_instance > n_vars) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Groth16Pk pk;
+  pk.pairing = pairing;
+  pk.n_constraints = n_constraints; pk.n_instance = n_instance; pk.n_vars = n_vars;
+  const uint64_t need = (uint64_t)n_constraints + n_instance;   // ark: domain over num_constraints + num_inputs
+  uint32_t log_n = 0;
+  while (((uint64_t)1 << log_n) < need) log_n++;
+  const int two_adicity = pairing == OZL_PAIRING_BN254 ? 28 : 32;
+  if ((int)log_n > two_adicity || log_n > 30) return OZL_ERR_DOMAIN;
+  pk.log_n = log_n;
+  const size_t n = (size_t)1 << log_n;
+  // handle sanity
+  Bases *ba, *bb1, *bb2, *bh, *bl;
+  for (auto hp : {std::make_pair(a_query, &ba), std::make_pair(b_g1_query, &bb1), std::make_pair(b_g2_query, &bb2),
+                  std::make_pair(h_query, &bh), std::make_pair(l_query, &bl)}) {
+    auto it = ctx->bases.find(hp.first);
+    if (it == ctx->bases.end()) return OZL_ERR_HANDLE;
+    *hp.second = &it->second;
+  }
+  if (ba->curve != g1_curve(pairing) || bb1->curve != g1_curve(pairing) || bh->curve != g1_curve(pairing) ||
+      bl->curve != g1_curve(pairing) || bb2->curve != g2_curve(pairing)) return OZL_ERR_ARG;
+  if (ba->n < n_vars || bb1->n < n_vars || bb2->n < n_vars || bh->n < n - 1 || bl->n < n_vars - n_instance) return OZL_ERR_ARG;
+  pk.h_a = a_query; pk.h_b1 = b_g1_query; pk.h_b2 = b_g2_query; pk.h_h = h_query; pk.h_l = l_query;
+  int r;
+  if ((r = upload_csr(ctx, A, &pk.A)) || (r = upload_csr(ctx, B, &pk.B)) || (r = upload_csr(ctx, C, &pk.C))) return r;
+  const int c1 = coord_u32(g1_curve(pairing)), c2 = coord_u32(g2_curve(pairing));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.coef, std::max<size_t>(n_coef, 1) * 32));
+  CUDA_TRY(ctx, cudaMemcpyAsync(pk.coef, coef_table, (size_t)n_coef * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.consts_g1, 3 * 3 * c1 * 4));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.consts_g2, 2 * 3 * c2 * 4));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.zinv, 64));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.z, (size_t)n_vars * 32));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.zc, (size_t)n_vars * 32));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.a, n * 32));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.b, n * 32));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.c, n * 32));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.hc, n * 32));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.acc, 16 * 3 * c2 * 4));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.rs, 16 * 32));
+  // constants: affine (host) -> Jacobian (device)
+  if ((r = ensure(ctx, ctx->out, 4096))) return r;
+  const uint64_t* g1c[3] = {alpha_g1, beta_g1, delta_g1};
+  for (int i = 0; i < 3; i++) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out.p, g1c[i], 2 * c1 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    g1_ops(pairing)->affine_to_jacobian(ctx->stream, (const uint32_t*)ctx->out.p, pk.consts_g1 + (size_t)i * 3 * c1);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  const uint64_t* g2c[2] = {beta_g2, delta_g2};
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out.p, g2c[i], 2 * c2 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    g2_ops(pairing)->affine_to_jacobian(ctx->stream, (const uint32_t*)ctx->out.p, pk.consts_g2 + (size_t)i * 3 * c2);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  field_ops(fr_field(pairing))->vanishing_inv(ctx->stream, (int)log_n, pk.zinv);
+  ctx->launches += 6;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *pk_handle = g_next_pk++;
+  pk_registry()[*pk_handle] = pk;
+  return OZL_OK;
+}
+
+int ozl_groth16_pk_destroy(ozl_ctx* ctx, uint32_t pk_handle) {
+  if (!ctx) return OZL_ERR_ARG;
+  auto it = pk_registry().find(pk_handle);
+  if (it == pk_registry().end()) return OZL_ERR_HANDLE;
+  destroy_pk(ctx, it->second);
+  pk_registry().erase(it);
+  return OZL_OK;
+}
+
+int ozl_groth16_domain_size(ozl_ctx* ctx, uint32_t pk_handle, uint32_t* out) {
+  if (!ctx || !out) return OZL_ERR_ARG;
+  auto it = pk_registry().find(pk_handle);
+  if (it == pk_registry().end()) return OZL_ERR_HANDLE;
+  *out = 1u << it->second.log_n;
+  return OZL_OK;
+}
+
+int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const uint64_t* r_scalar, const uint64_t* s_scalar,
+                      uint64_t* proof_a, uint64_t* proof_b, uint64_t* proof_c, uint64_t* h_out) {
+  if (!ctx || !z || !r_scalar || !s_scalar || !proof_a || !proof_b || !proof_c) return OZL_ERR_ARG;
+  auto it = pk_registry().find(pk_handle);
+  if (it == pk_registry().end()) return OZL_ERR_HANDLE;
+  Groth16Pk& pk = it->second;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const OzlFieldOps* f = field_ops(fr_field(pk.pairing));
+  const OzlCurveOps* o1 = g1_ops(pk.pairing);
+  const OzlCurveOps* o2 = g2_ops(pk.pairing);
+  const int c1 = coord_u32(g1_curve(pk.pairing)), c2 = coord_u32(g2_curve(pk.pairing));
+  const int J1 = 3 * c1, J2 = 3 * c2;  // u32 per Jacobian point
+  const size_t n = (size_t)1 << pk.log_n;
+  cudaStream_t st = ctx->stream;
+  const uint32_t nc = pk.n_constraints, ni = pk.n_instance, m = pk.n_vars;
+  int rc;
+  if (ctx->timing) stages_clear(ctx);
+
+  STAGE(ctx, "g16_h2d_witness");
+  CUDA_TRY(ctx, cudaMemcpyAsync(pk.z, z, (size_t)m * 32, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(pk.rs, r_scalar, 32, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(pk.rs + 8, s_scalar, 32, cudaMemcpyHostToDevice, st));
+  STAGE_END(ctx);
+
+  STAGE(ctx, "g16_matvec");
+  CUDA_TRY(ctx, cudaMemsetAsync(pk.a, 0, n * 32, st));
+  CUDA_TRY(ctx, cudaMemsetAsync(pk.b, 0, n * 32, st));
+  CUDA_TRY(ctx, cudaMemsetAsync(pk.c, 0, n * 32, st));
+  f->spmv(st, pk.A.row_ptr, pk.A.col, pk.A.cidx, pk.coef, pk.z, nc, pk.a);
+  f->spmv(st, pk.B.row_ptr, pk.B.col, pk.B.cidx, pk.coef, pk.z, nc, pk.b);
+  f->spmv(st, pk.C.row_ptr, pk.C.col, pk.C.cidx, pk.coef, pk.z, nc, pk.c);
+  ctx->launches += 3;
+  // ark: a[num_constraints + j] = full_assignment[j] for the num_inputs instance variables
+  CUDA_TRY(ctx, cudaMemcpyAsync(pk.a + (size_t)nc * 8, pk.z, (size_t)ni * 32, cudaMemcpyDeviceToDevice, st));
+  f->from_mont(st, pk.z, pk.zc, m);
+  ctx->launches += 1;
+  STAGE_END(ctx);
+
+  STAGE(ctx, "g16_ntt");
+  int launches = 0;
+  NttWorkspace& ws = ctx->ntt_ws;
+  uint32_t* vecs[3] = {pk.a, pk.b, pk.c};
+  for (int i = 0; i < 3; i++) if ((rc = f->ntt(st, ws, vecs[i], pk.log_n, true, false, &launches))) goto ntt_fail;
+  for (int i = 0; i < 3; i++) if ((rc = f->ntt(st, ws, vecs[i], pk.log_n, false, true, &launches))) goto ntt_fail;
+  f->h_pointwise(st, pk.a, pk.b, pk.c, pk.zinv, (uint32_t)n);
+  launches++;
+  if ((rc = f->ntt(st, ws, pk.a, pk.log_n, true, true, &launches))) goto ntt_fail;
+  f->from_mont(st, pk.a, pk.hc, (uint32_t)n);
+  launches++;
+  ctx->launches += launches;
+  if (ctx->timing && !ctx->stages.empty()) ctx->stages.back().launches += launches;
+  STAGE_END(ctx);
+  if (h_out) CUDA_TRY(ctx, cudaMemcpyAsync(h_out, pk.a, n * 32, cudaMemcpyDeviceToHost, st));
+
+  {
+    // MSM outputs (Jacobian): acc[0]=h, [1]=l, [2]=a, [3]=b1 in G1 slots; b2 in a G2 slot after them
+    uint32_t* acc = pk.acc;
+    uint32_t* acc_g2 = pk.acc + 6 * J2;
+    auto& reg = ctx->bases;
+    if ((rc = ozl_rt_msm(ctx, reg[pk.h_h], pk.hc, n - 1, acc + 0 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, reg[pk.h_l], pk.zc + (size_t)ni * 8, m - ni, acc + 1 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, reg[pk.h_a], pk.zc, m, acc + 2 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, reg[pk.h_b1], pk.zc, m, acc + 3 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, reg[pk.h_b2], pk.zc, m, acc_g2))) return rc;
+
+    STAGE(ctx, "g16_assemble");
+    // scalars: rs[0]=r, rs[1]=s, rs[2]=1
+    static const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(pk.rs + 16, one, 32, cudaMemcpyHostToDevice, st));
+    uint32_t* sc = pk.rs + 32;            // scalar lists for lincomb
+    uint32_t* pts = acc + 4 * J1;         // G1 point lists (4 slots) ; results after
+    // A = alpha1 + a_acc + r delta1
+    auto cp = [&](uint32_t* dst, const uint32_t* src, size_t words) { return cudaMemcpyAsync(dst, src, words * 4, cudaMemcpyDeviceToDevice, st); };
+    CUDA_TRY(ctx, cp(pts + 0 * J1, pk.consts_g1 + 0 * J1, J1));
+    CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 2 * J1, J1));
+    CUDA_TRY(ctx, cp(pts + 2 * J1, pk.consts_g1 + 2 * J1, J1));
+    CUDA_TRY(ctx, cp(sc + 0, pk.rs + 16, 8));
+    CUDA_TRY(ctx, cp(sc + 8, pk.rs + 16, 8));
+    CUDA_TRY(ctx, cp(sc + 16, pk.rs + 0, 8));
+    uint32_t* A_jac = acc + 8 * J1;             // G1 results: slots 8, 9, 10
+    uint32_t* D_jac = A_jac + J1;
+    uint32_t* C_jac = D_jac + J1;
+    o1->lincomb(st, pts, sc, 3, A_jac);
+    // D = beta1 + b1_acc
+    CUDA_TRY(ctx, cp(pts + 0 * J1, pk.consts_g1 + 1 * J1, J1));
+    CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 3 * J1, J1));
+    o1->lincomb(st, pts, sc, 2, D_jac);
+    // C = l_acc + h_acc + s A + r D
+    CUDA_TRY(ctx, cp(pts + 0 * J1, acc + 1 * J1, J1));
+    CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 0 * J1, J1));
+    CUDA_TRY(ctx, cp(pts + 2 * J1, A_jac, J1));
+    CUDA_TRY(ctx, cp(pts + 3 * J1, D_jac, J1));
+    CUDA_TRY(ctx, cp(sc + 16, pk.rs + 8, 8));
+    CUDA_TRY(ctx, cp(sc + 24, pk.rs + 0, 8));
+    o1->lincomb(st, pts, sc, 4, C_jac);
+    // B = beta2 + b2_acc + s delta2   (G2)
+    uint32_t* pts2 = acc_g2 + J2;
+    uint32_t* B_jac = pts2 + 3 * J2;
+    CUDA_TRY(ctx, cp(pts2 + 0 * J2, pk.consts_g2 + 0 * J2, J2));
+    CUDA_TRY(ctx, cp(pts2 + 1 * J2, acc_g2, J2));
+    CUDA_TRY(ctx, cp(pts2 + 2 * J2, pk.consts_g2 + 1 * J2, J2));
+    CUDA_TRY(ctx, cp(sc + 16, pk.rs + 8, 8));
+    o2->lincomb(st, pts2, sc, 3, B_jac);
+    // affine outputs
+    if ((rc = ensure(ctx, ctx->out, 4096))) return rc;
+    uint32_t* outb = (uint32_t*)ctx->out.p;
+    int* flags = (int*)(outb + 512);
+    o1->jacobian_to_affine(st, A_jac, outb, flags);
+    o1->jacobian_to_affine(st, C_jac, outb + 2 * c1, flags + 1);
+    o2->jacobian_to_affine(st, B_jac, outb + 4 * c1, flags + 2);
+    ctx->launches += 7;
+    STAGE_END(ctx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(proof_a, outb, 2 * c1 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(proof_c, outb + 2 * c1, 2 * c1 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(proof_b, outb + 4 * c1, 2 * c2 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->last_error = std::string("groth16_prove: ") + cudaGetErrorString(e); return OZL_ERR_CUDA; }
+  }
+  return OZL_OK;
+
+ntt_fail:
+  if (rc == -2) return OZL_ERR_DOMAIN;
+  if (rc == -4) return OZL_ERR_OOM;
+  ctx->last_error = "groth16_prove: ntt launch failed";
+  return OZL_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -425,6 +425,75 @@ k_generate_bases(uint64_t start, uint32_t n, uint32_t* __restrict__ out) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// fixed-base scalar multiplication [k_j] G for a vector of scalars (known-trapdoor Groth16 setup:
+// ark_groth16::generate_parameters builds every query vector this way) -- plain double-and-add,
+// one thread per scalar, one inversion per thread for the affine output.  Setup path, not hot.
+// ---------------------------------------------------------------------------------------------
+template <class F, class C>
+__global__ void __launch_bounds__(128)
+k_fixed_base_mul(const uint32_t* __restrict__ scalars, uint32_t n, uint32_t* __restrict__ out, uint8_t* __restrict__ flags) {
+  constexpr int AFF = 2 * F::N;
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Affine<F> g;
+  g.x = F::from_limbs(C::gx());
+  g.y = F::from_limbs(C::gy());
+  uint32_t s[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) s[i] = scalars[(size_t)j * 8 + i];
+  XYZZ<F> acc = XYZZ<F>::identity();
+  for (int bit = 255; bit >= 0; bit--) {
+    acc = acc.dbl();
+    if ((s[bit >> 5] >> (bit & 31)) & 1) acc.add_mixed_cold(g);
+  }
+  Affine<F> a;
+  a.x = F::zero(); a.y = F::zero();
+  const bool ok = acc.to_affine(a);
+  flags[j] = ok ? 0 : 1;
+  a.x.store(out + (size_t)j * AFF);
+  a.y.store(out + (size_t)j * AFF + F::N);
+}
+
+// out = sum_{i<k} s_i * P_i for a handful of Jacobian points (Groth16 proof assembly:
+// A = alpha + a_acc + r*delta etc.).  Lane i computes s_i * P_i by double-and-add, then the warp
+// sums with a shuffle tree.  One warp.
+template <class F>
+__global__ void __launch_bounds__(32)
+k_lincomb(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars, uint32_t k, uint32_t* __restrict__ out_jac) {
+  const uint32_t lane = threadIdx.x;
+  XYZZ<F> acc = XYZZ<F>::identity();
+  if (lane < k) {
+    const XYZZ<F> p = xyzz_from_jacobian<F>(pts + (size_t)lane * 3 * F::N);
+    uint32_t s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = scalars[(size_t)lane * 8 + i];
+    int top = 255;
+    while (top > 0 && !((s[top >> 5] >> (top & 31)) & 1)) top--;
+    for (int bit = top; bit >= 0; bit--) {
+      acc = acc.dbl();
+      if ((s[bit >> 5] >> (bit & 31)) & 1) acc.add(p);
+    }
+  }
+  for (int d = 16; d >= 1; d >>= 1) {
+    XYZZ<F> o = shfl_down_xyzz(acc, d);
+    if (lane < (uint32_t)d) acc.add(o);
+  }
+  if (lane == 0) {
+    F X, Y, Z;
+    acc.to_jacobian(X, Y, Z);
+    X.store(out_jac); Y.store(out_jac + F::N); Z.store(out_jac + 2 * F::N);
+  }
+}
+
+template <class F>
+__global__ void k_affine_to_jacobian(const uint32_t* __restrict__ aff, uint32_t* __restrict__ out_jac) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  F::load(aff).store(out_jac);
+  F::load(aff + F::N).store(out_jac + F::N);
+  F::one().store(out_jac + 2 * F::N);
+}
+
+// ---------------------------------------------------------------------------------------------
 // field multiplier micro-benchmark (the practical fma-pipe roofline of every kernel above)
 // ---------------------------------------------------------------------------------------------
 template <class F>

@@ -32,14 +32,16 @@ struct NttConsts {
   Fp<P> one;
 };
 
+// Device tables are kept per direction (index 0 = forward, 1 = inverse) so a prover that
+// alternates ifft / coset_fft / coset_ifft on one domain builds each table once.
 struct NttWorkspace {
   void* scratch = nullptr; size_t scratch_cap = 0;
-  void* tw = nullptr; size_t tw_cap = 0;
-  void* glo = nullptr; size_t glo_cap = 0;
-  void* ghi = nullptr; size_t ghi_cap = 0;
-  void* consts = nullptr;
-  int key_field = -1, key_log_n = -1, key_inverse = -1;   // what tw/consts currently hold
-  int coset_key_field = -1, coset_key_log_n = -1, coset_key_inverse = -1;
+  void* tw[2] = {nullptr, nullptr}; size_t tw_cap[2] = {0, 0};
+  void* glo[2] = {nullptr, nullptr}; size_t glo_cap[2] = {0, 0};
+  void* ghi[2] = {nullptr, nullptr}; size_t ghi_cap[2] = {0, 0};
+  void* consts[2] = {nullptr, nullptr};
+  int key_field[2] = {-1, -1}, key_log_n[2] = {-1, -1};              // what tw/consts currently hold
+  int coset_key_field[2] = {-1, -1}, coset_key_log_n[2] = {-1, -1};
 };
 
 template <class P>
@@ -162,34 +164,35 @@ int ntt_run(cudaStream_t st, NttWorkspace& ws, int field_id, uint32_t* d_data, u
   if (log_n > P::TWO_ADICITY || log_n > 30) return -2;
   if (log_n == 0) return 0;  // size-1 domain: identity (size_inv = 1, g^0 = 1)
   const size_t n = (size_t)1 << log_n;
+  const int dir = inverse ? 1 : 0;
   if (ntt_ensure(&ws.scratch, &ws.scratch_cap, n * F::N * 4)) return -4;
-  if (ntt_ensure(&ws.tw, &ws.tw_cap, std::max<size_t>(n / 2, 1) * F::N * 4)) return -4;
-  if (!ws.consts && cudaMalloc(&ws.consts, 4096) != cudaSuccess) return -4;
-  NttConsts<P>* consts = (NttConsts<P>*)ws.consts;
-  uint32_t* tw = (uint32_t*)ws.tw;
+  if (ntt_ensure(&ws.tw[dir], &ws.tw_cap[dir], std::max<size_t>(n / 2, 1) * F::N * 4)) return -4;
+  if (!ws.consts[dir] && cudaMalloc(&ws.consts[dir], 4096) != cudaSuccess) return -4;
+  NttConsts<P>* consts = (NttConsts<P>*)ws.consts[dir];
+  uint32_t* tw = (uint32_t*)ws.tw[dir];
 
-  if (ws.key_field != field_id || ws.key_log_n != log_n || ws.key_inverse != (int)inverse) {
+  if (ws.key_field[dir] != field_id || ws.key_log_n[dir] != log_n) {
     k_ntt_setup<P><<<1, 32, 0, st>>>(log_n, inverse ? 1 : 0, consts);
     const uint32_t cnt = (uint32_t)(n / 2);
     const uint32_t threads = (cnt + POW_RUN - 1) / POW_RUN;
     k_build_powers<P><<<(threads + 127) / 128, 128, 0, st>>>(&consts->omega, &consts->one, cnt, tw);
     *launches += 2;
-    ws.key_field = field_id; ws.key_log_n = log_n; ws.key_inverse = (int)inverse;
-    ws.coset_key_field = -1;
+    ws.key_field[dir] = field_id; ws.key_log_n[dir] = log_n;
+    ws.coset_key_field[dir] = -1;
   }
   const int lo_bits = log_n < NTT_LO_BITS ? log_n : NTT_LO_BITS;
-  if (coset && (ws.coset_key_field != field_id || ws.coset_key_log_n != log_n || ws.coset_key_inverse != (int)inverse)) {
+  if (coset && (ws.coset_key_field[dir] != field_id || ws.coset_key_log_n[dir] != log_n)) {
     const uint32_t nlo = 1u << lo_bits, nhi = 1u << (log_n - lo_bits);
-    if (ntt_ensure(&ws.glo, &ws.glo_cap, (size_t)nlo * F::N * 4)) return -4;
-    if (ntt_ensure(&ws.ghi, &ws.ghi_cap, (size_t)nhi * F::N * 4)) return -4;
-    k_build_powers<P><<<((nlo + POW_RUN - 1) / POW_RUN + 127) / 128, 128, 0, st>>>(&consts->g, &consts->one, nlo, (uint32_t*)ws.glo);
+    if (ntt_ensure(&ws.glo[dir], &ws.glo_cap[dir], (size_t)nlo * F::N * 4)) return -4;
+    if (ntt_ensure(&ws.ghi[dir], &ws.ghi_cap[dir], (size_t)nhi * F::N * 4)) return -4;
+    k_build_powers<P><<<((nlo + POW_RUN - 1) / POW_RUN + 127) / 128, 128, 0, st>>>(&consts->g, &consts->one, nlo, (uint32_t*)ws.glo[dir]);
     // inverse coset: fold size_inv into the high table
-    k_build_powers<P><<<((nhi + POW_RUN - 1) / POW_RUN + 127) / 128, 128, 0, st>>>(&consts->g_hi, inverse ? &consts->size_inv : &consts->one, nhi, (uint32_t*)ws.ghi);
+    k_build_powers<P><<<((nhi + POW_RUN - 1) / POW_RUN + 127) / 128, 128, 0, st>>>(&consts->g_hi, inverse ? &consts->size_inv : &consts->one, nhi, (uint32_t*)ws.ghi[dir]);
     *launches += 2;
-    ws.coset_key_field = field_id; ws.coset_key_log_n = log_n; ws.coset_key_inverse = (int)inverse;
+    ws.coset_key_field[dir] = field_id; ws.coset_key_log_n[dir] = log_n;
   }
-  const uint32_t* glo = (const uint32_t*)ws.glo;
-  const uint32_t* ghi = (const uint32_t*)ws.ghi;
+  const uint32_t* glo = (const uint32_t*)ws.glo[dir];
+  const uint32_t* ghi = (const uint32_t*)ws.ghi[dir];
 
   // pass plan: radix-8 passes, remainder first
   int radices[16], np = 0;

@@ -262,4 +262,21 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   return OZL_OK;
 }
 
+inline const OzlCurveOps* curve_ops_for(int curve) {
+  switch (curve) {
+    case OZL_BLS12_381_G1: return &ozl_ops_bls12_381_g1;
+    case OZL_BLS12_381_G2: return &ozl_ops_bls12_381_g2;
+    case OZL_BN254_G1: return &ozl_ops_bn254_g1;
+    case OZL_BN254_G2: return &ozl_ops_bn254_g2;
+  }
+  return nullptr;
+}
+
+// MSM over the first n bases of b with device scalars / device output, enqueued on ctx->stream.
+inline int ozl_rt_msm(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
+  const OzlCurveOps* ops = curve_ops_for(b.curve);
+  if (!ops || n > b.n) return OZL_ERR_ARG;
+  return ops->msm(ctx, b, d_scalars, n, d_out);
+}
+
 }  // namespace ozl_rt
