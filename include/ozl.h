@@ -75,8 +75,10 @@ const char* ozl_last_error(const ozl_ctx* ctx);
 int ozl_ctx_create(int device, ozl_ctx** out);
 void ozl_ctx_destroy(ozl_ctx* ctx);
 /* Run on a caller-supplied cudaStream_t (passed as void*), e.g. torch's current stream, so the
- * caller can bracket calls with its own CUDA events.  NULL restores the context's own stream. */
+ * caller can bracket calls with its own CUDA events.  NULL is CUDA's legacy default stream;
+ * ozl_ctx_use_own_stream goes back to the context's private stream. */
 int ozl_ctx_set_stream(ozl_ctx* ctx, void* cuda_stream);
+int ozl_ctx_use_own_stream(ozl_ctx* ctx);
 void* ozl_ctx_get_stream(ozl_ctx* ctx);
 int ozl_ctx_synchronize(ozl_ctx* ctx);
 /* Bytes of u64 limbs per coordinate / per affine point / per Jacobian point of a curve. */
@@ -94,6 +96,11 @@ int ozl_msm_bases_upload_device(ozl_ctx* ctx, int curve, const uint64_t* d_bases
 /* Synthesize bases P_i = [start + i]G (G = the curve's generator) directly in device memory;
  * used by benchmarks and size-independent parity checks (sum s_i P_i = [sum s_i (start+i)]G). */
 int ozl_msm_bases_generate(ozl_ctx* ctx, int curve, uint64_t start, size_t n, uint32_t* handle);
+/* Trade HBM for work: store `factor` copies 2^(c*Wc*q) * P_i of the bases (q < factor,
+ * Wc = ceil(W / factor) windows per copy) so that only Wc bucket sets are reduced and the final
+ * Horner shrinks by the same factor.  One-time cost at key-load time; the window width c is
+ * fixed from the handle's size at this point.  Results are unchanged (same group element). */
+int ozl_msm_bases_precompute(ozl_ctx* ctx, uint32_t handle, int factor);
 /* Copy bases [first, first + n) of a handle back to the host (packed affine, Montgomery). */
 int ozl_msm_bases_download(ozl_ctx* ctx, uint32_t handle, size_t first, size_t n, uint64_t* out);
 int ozl_msm_bases_free(ozl_ctx* ctx, uint32_t handle);

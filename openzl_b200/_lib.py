@@ -23,9 +23,9 @@ FIELD_IDS = {"bn254_fr": 0, "bls12_381_fr": 1}
 
 # every symbol include/ozl.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "ozl_version", "ozl_strerror", "ozl_last_error", "ozl_ctx_create", "ozl_ctx_destroy", "ozl_ctx_set_stream",
+    "ozl_version", "ozl_strerror", "ozl_last_error", "ozl_ctx_create", "ozl_ctx_destroy", "ozl_ctx_set_stream", "ozl_ctx_use_own_stream",
     "ozl_ctx_get_stream", "ozl_ctx_synchronize", "ozl_curve_coord_limbs", "ozl_msm_bases_upload",
-    "ozl_msm_bases_upload_device", "ozl_msm_bases_generate", "ozl_msm_bases_download", "ozl_msm_bases_free",
+    "ozl_msm_bases_upload_device", "ozl_msm_bases_generate", "ozl_msm_bases_precompute", "ozl_msm_bases_download", "ozl_msm_bases_free",
     "ozl_msm", "ozl_msm_device_async", "ozl_msm_set_window_bits", "ozl_msm_get_window_bits", "ozl_jacobian_sum",
     "ozl_jacobian_to_affine", "ozl_ntt", "ozl_ntt_device_async", "ozl_ctx_enable_timing",
     "ozl_ctx_get_stage_times", "ozl_ctx_launch_count", "ozl_bench_field_mul", "ozl_fr_spmv", "ozl_fixed_base_mul",
@@ -80,6 +80,7 @@ def load() -> ctypes.CDLL:
     lib.ozl_ctx_destroy.argtypes = [vp]
     lib.ozl_ctx_destroy.restype = None
     lib.ozl_ctx_set_stream.argtypes = [vp, vp]
+    lib.ozl_ctx_use_own_stream.argtypes = [vp]
     lib.ozl_ctx_get_stream.argtypes = [vp]
     lib.ozl_ctx_get_stream.restype = vp
     lib.ozl_ctx_synchronize.argtypes = [vp]
@@ -87,6 +88,7 @@ def load() -> ctypes.CDLL:
     lib.ozl_msm_bases_upload.argtypes = [vp, ctypes.c_int, vp, vp, sz, u32p]
     lib.ozl_msm_bases_upload_device.argtypes = [vp, ctypes.c_int, vp, vp, sz, u32p]
     lib.ozl_msm_bases_generate.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, sz, u32p]
+    lib.ozl_msm_bases_precompute.argtypes = [vp, ctypes.c_uint32, ctypes.c_int]
     lib.ozl_msm_bases_download.argtypes = [vp, ctypes.c_uint32, sz, sz, vp]
     lib.ozl_msm_bases_free.argtypes = [vp, ctypes.c_uint32]
     lib.ozl_msm.argtypes = [vp, ctypes.c_uint32, vp, sz, vp]

@@ -55,7 +55,11 @@ class Context:
         self.close()
 
     def set_stream(self, cuda_stream_ptr: Optional[int]):
-        self._check(self._lib.ozl_ctx_set_stream(self._h, cuda_stream_ptr), "ozl_ctx_set_stream")
+        """Run on the given cudaStream_t (0 / None = CUDA's legacy default stream)."""
+        self._check(self._lib.ozl_ctx_set_stream(self._h, cuda_stream_ptr or None), "ozl_ctx_set_stream")
+
+    def use_own_stream(self):
+        self._check(self._lib.ozl_ctx_use_own_stream(self._h), "ozl_ctx_use_own_stream")
 
     def use_torch_stream(self, stream=None):
         """Run on a torch CUDA stream (default: the current one) so torch events bracket our kernels."""
@@ -164,6 +168,11 @@ class Bases:
         if self.handle and self.ctx._h:
             self.ctx._lib.ozl_msm_bases_free(self.ctx._h, self.handle)
         self.handle = 0
+
+    def precompute(self, factor: int) -> "Bases":
+        """Store `factor` shifted copies of the bases (fewer bucket sets / shorter final Horner)."""
+        self.ctx._check(self.ctx._lib.ozl_msm_bases_precompute(self.ctx._h, self.handle, factor), "ozl_msm_bases_precompute")
+        return self
 
     def download(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
         n = self.n - first if n is None else n

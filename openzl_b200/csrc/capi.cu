@@ -111,7 +111,13 @@ void ozl_ctx_destroy(ozl_ctx* ctx) {
 int ozl_ctx_set_stream(ozl_ctx* ctx, void* s) {
   if (!ctx) return OZL_ERR_ARG;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  ctx->stream = (cudaStream_t)s;   // NULL is CUDA's legacy default stream
+  return OZL_OK;
+}
+int ozl_ctx_use_own_stream(ozl_ctx* ctx) {
+  if (!ctx) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = ctx->own_stream;
   return OZL_OK;
 }
 void* ozl_ctx_get_stream(ozl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -202,6 +208,42 @@ int ozl_msm_bases_free(ozl_ctx* ctx, uint32_t handle) {
   return OZL_OK;
 }
 
+int ozl_msm_bases_precompute(ozl_ctx* ctx, uint32_t handle, int factor) {
+  if (!ctx || factor < 1 || factor > 16) return OZL_ERR_ARG;
+  Bases* b;
+  int r = find_bases(ctx, handle, &b);
+  if (r) return r;
+  if (b->factor != 1) return OZL_ERR_ARG;  // already precomputed
+  if (factor == 1 || b->n == 0) return OZL_OK;
+  if ((uint64_t)b->n * factor >= 0x7fffffffull) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const MsmPlan p = make_plan(b->curve, b->n, ctx->forced_c);
+  const int Wc = (p.W + factor - 1) / factor;
+  const int copies = (p.W + Wc - 1) / Wc;
+  const size_t stride = (size_t)b->n * 2 * coord_u32(b->curve);
+  uint32_t* nd = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void**)&nd, stride * copies * 4));
+  CUDA_TRY(ctx, cudaMemcpyAsync(nd, b->d_pts, stride * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  const OzlCurveOps* ops = curve_ops(b->curve);
+  for (int q = 1; q < copies; q++) {
+    ops->precompute(ctx->stream, nd + (size_t)(q - 1) * stride, nd + (size_t)q * stride, (uint32_t)b->n, p.c * Wc);
+    ctx->launches++;
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(nd);
+    ctx->last_error = std::string("bases_precompute: ") + cudaGetErrorString(e);
+    return OZL_ERR_CUDA;
+  }
+  cudaFree(b->d_pts);
+  b->d_pts = nd;
+  b->factor = copies;
+  b->pc = p.c;
+  b->pWc = Wc;
+  return OZL_OK;
+}
+
 // ---- msm ------------------------------------------------------------------------------------
 int ozl_msm_device_async(ozl_ctx* ctx, uint32_t handle, const uint64_t* d_scalars, size_t n, uint64_t* d_out) {
   if (!ctx || !d_out || (!d_scalars && n)) return OZL_ERR_ARG;
@@ -244,6 +286,7 @@ int ozl_msm_get_window_bits(ozl_ctx* ctx, int curve, size_t n) {
   if (!ctx || !coord_u32(curve)) return -1;
   return make_plan(curve, n, ctx->forced_c).c;
 }
+
 
 int ozl_jacobian_sum(ozl_ctx* ctx, int curve, const uint64_t* points, size_t k, uint64_t* out_jacobian) {
   if (!ctx || !out_jacobian || (!points && k) || !coord_u32(curve)) return OZL_ERR_ARG;

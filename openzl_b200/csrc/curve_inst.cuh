@@ -27,9 +27,22 @@ void fixed_base_entry(cudaStream_t st, const uint32_t* d_scalars, uint32_t n, ui
 void lincomb_entry(cudaStream_t st, const uint32_t* d_pts, const uint32_t* d_scalars, uint32_t k, uint32_t* d_out) {
   k_lincomb<F_><<<1, 32, 0, st>>>(d_pts, d_scalars, k, d_out);
 }
+void smul_var_entry(cudaStream_t st, const uint32_t* d_pts, const uint32_t* d_scalars, uint32_t k, uint32_t* d_out) {
+  if (k) k_scalar_mul_warp<F_, false><<<k, 32, 0, st>>>(d_pts, d_scalars, d_out);
+}
+void smul_table_entry(cudaStream_t st, const uint32_t* d_tables, const uint32_t* d_scalars, uint32_t k, uint32_t* d_out) {
+  if (k) k_scalar_mul_warp<F_, true><<<k, 32, 0, st>>>(d_tables, d_scalars, d_out);
+}
+void build_table_entry(cudaStream_t st, const uint32_t* d_pt, uint32_t* d_table) {
+  k_build_byte_table<F_><<<1, 32, 0, st>>>(d_pt, d_table);
+}
+void precompute_entry(cudaStream_t st, const uint32_t* d_src, uint32_t* d_dst, uint32_t n, int shift) {
+  const uint32_t threads = (n + GEN_RUN - 1) / GEN_RUN;
+  k_precompute<F_><<<(threads + 127) / 128, 128, 0, st>>>(d_src, d_dst, n, shift);
+}
 void a2j_entry(cudaStream_t st, const uint32_t* d_aff, uint32_t* d_out) {
   k_affine_to_jacobian<F_><<<1, 32, 0, st>>>(d_aff, d_out);
 }
 }  // namespace
 
-const OzlCurveOps OZL_OPS = {msm_entry, generate_entry, jsum_entry, jaff_entry, bench_entry, fixed_base_entry, lincomb_entry, a2j_entry};
+const OzlCurveOps OZL_OPS = {msm_entry, generate_entry, jsum_entry, jaff_entry, bench_entry, fixed_base_entry, lincomb_entry, smul_var_entry, smul_table_entry, build_table_entry, precompute_entry, a2j_entry};

@@ -23,6 +23,13 @@ struct OzlCurveOps {
   void (*fixed_base_mul)(cudaStream_t st, const uint32_t* d_scalars, uint32_t n, uint32_t* d_out_affine, uint8_t* d_flags);
   // out_jac = sum_{i<k} scalars[i] * pts_jac[i]   (k <= 32; one lane per term)
   void (*lincomb)(cudaStream_t st, const uint32_t* d_pts_jac, const uint32_t* d_scalars, uint32_t k, uint32_t* d_out_jac);
+  // out[b] = scalars[b] * P_b for k Jacobian points, one warp each (variable points)
+  void (*scalar_mul_var)(cudaStream_t st, const uint32_t* d_pts_jac, const uint32_t* d_scalars, uint32_t k, uint32_t* d_out_jac);
+  // same with per-point byte tables (32 Jacobian entries each) built by build_byte_table
+  void (*scalar_mul_table)(cudaStream_t st, const uint32_t* d_tables, const uint32_t* d_scalars, uint32_t k, uint32_t* d_out_jac);
+  void (*build_byte_table)(cudaStream_t st, const uint32_t* d_pt_jac, uint32_t* d_table);
+  // dst_i = 2^shift * src_i for n affine points (base precomputation)
+  void (*precompute)(cudaStream_t st, const uint32_t* d_src, uint32_t* d_dst, uint32_t n, int shift);
   // Jacobian <- affine (x||y) on the device, for constants uploaded from the host
   void (*affine_to_jacobian)(cudaStream_t st, const uint32_t* d_aff, uint32_t* d_out_jac);
 };
@@ -39,6 +46,8 @@ struct OzlFieldOps {
   void (*from_mont)(cudaStream_t st, const uint32_t* in, uint32_t* out, uint32_t n);
   void (*h_pointwise)(cudaStream_t st, uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* scale, uint32_t n);
   void (*vanishing_inv)(cudaStream_t st, int log_n, uint32_t* out);
+  // out = a * b mod r, all canonical 256-bit integers on the device
+  void (*mul_canonical)(cudaStream_t st, const uint32_t* a, const uint32_t* b, uint32_t* out);
 };
 extern const OzlFieldOps ozl_fops_bn254_fr;
 extern const OzlFieldOps ozl_fops_bls12_381_fr;

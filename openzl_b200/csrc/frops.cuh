@@ -60,4 +60,15 @@ __global__ void k_vanishing_inv(int log_n, Fp<P>* out) {
   *out = (g - F::one()).inverse();
 }
 
+// out = a * b mod r on canonical integers (r*s for the proof assembly)
+template <class P>
+__global__ void k_mul_canonical(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  typedef Fp<P> F;
+  F x = F::from_limbs(a).to_mont(), y = F::from_limbs(b).to_mont();
+  F r = (x * y).from_mont();
+#pragma unroll
+  for (int i = 0; i < F::N; i++) out[i] = r.v[i];
+}
+
 }  // namespace ozl

@@ -25,6 +25,8 @@ struct Groth16Pk {
   uint32_t h_a = 0, h_b1 = 0, h_b2 = 0, h_h = 0, h_l = 0;
   uint32_t* consts_g1 = nullptr;  // Jacobian alpha1, beta1, delta1
   uint32_t* consts_g2 = nullptr;  // Jacobian beta2, delta2
+  uint32_t* tables_g1 = nullptr;  // byte tables (32 Jacobian entries each) of alpha1, beta1, delta1, delta1
+  uint32_t* tables_g2 = nullptr;  // byte table of delta2
   uint32_t* zinv = nullptr;       // 1/(g^n - 1)
   // per-proof workspace
   uint32_t *z = nullptr, *zc = nullptr, *a = nullptr, *b = nullptr, *c = nullptr, *hc = nullptr;
@@ -71,7 +73,7 @@ int fr_field(int pairing) { return pairing == OZL_PAIRING_BN254 ? OZL_BN254_FR :
 void destroy_pk(ozl_ctx* ctx, Groth16Pk& pk) {
   cudaStreamSynchronize(ctx->stream);
   free_csr(pk.A); free_csr(pk.B); free_csr(pk.C);
-  void* ptrs[] = {pk.coef, pk.consts_g1, pk.consts_g2, pk.zinv, pk.z, pk.zc, pk.a, pk.b, pk.c, pk.hc, pk.acc, pk.rs};
+  void* ptrs[] = {pk.tables_g1, pk.tables_g2, pk.coef, pk.consts_g1, pk.consts_g2, pk.zinv, pk.z, pk.zc, pk.a, pk.b, pk.c, pk.hc, pk.acc, pk.rs};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (uint32_t h : {pk.h_a, pk.h_b1, pk.h_b2, pk.h_h, pk.h_l}) ozl_msm_bases_free(ctx, h);
 }
@@ -184,8 +186,8 @@ int ozl_groth16_pk_create(ozl_ctx* ctx, int pairing, uint32_t n_constraints, uin
   CUDA_TRY(ctx, cudaMalloc((void**)&pk.b, n * 32));
   CUDA_TRY(ctx, cudaMalloc((void**)&pk.c, n * 32));
   CUDA_TRY(ctx, cudaMalloc((void**)&pk.hc, n * 32));
-  CUDA_TRY(ctx, cudaMalloc((void**)&pk.acc, 16 * 3 * c2 * 4));
-  CUDA_TRY(ctx, cudaMalloc((void**)&pk.rs, 16 * 32));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.acc, 24 * 3 * c2 * 4));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.rs, 32 * 32));
   // constants: affine (host) -> Jacobian (device)
   if ((r = ensure(ctx, ctx->out, 4096))) return r;
   const uint64_t* g1c[3] = {alpha_g1, beta_g1, delta_g1};
@@ -199,6 +201,16 @@ int ozl_groth16_pk_create(ozl_ctx* ctx, int pairing, uint32_t n_constraints, uin
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out.p, g2c[i], 2 * c2 * 4, cudaMemcpyHostToDevice, ctx->stream));
     g2_ops(pairing)->affine_to_jacobian(ctx->stream, (const uint32_t*)ctx->out.p, pk.consts_g2 + (size_t)i * 3 * c2);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  // byte tables for the fixed points of the proof assembly: alpha1, beta1, delta1, delta1 | delta2
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.tables_g1, (size_t)4 * 32 * 3 * c1 * 4));
+  CUDA_TRY(ctx, cudaMalloc((void**)&pk.tables_g2, (size_t)1 * 32 * 3 * c2 * 4));
+  {
+    const int order[4] = {0, 1, 2, 2};
+    for (int i = 0; i < 4; i++)
+      g1_ops(pairing)->build_byte_table(ctx->stream, pk.consts_g1 + (size_t)order[i] * 3 * c1, pk.tables_g1 + (size_t)i * 32 * 3 * c1);
+    g2_ops(pairing)->build_byte_table(ctx->stream, pk.consts_g2 + (size_t)1 * 3 * c2, pk.tables_g2);
+    ctx->launches += 5;
   }
   field_ops(fr_field(pairing))->vanishing_inv(ctx->stream, (int)log_n, pk.zinv);
   ctx->launches += 6;
@@ -282,7 +294,7 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
   {
     // MSM outputs (Jacobian): acc[0]=h, [1]=l, [2]=a, [3]=b1 in G1 slots; b2 in a G2 slot after them
     uint32_t* acc = pk.acc;
-    uint32_t* acc_g2 = pk.acc + 6 * J2;
+    uint32_t* acc_g2 = pk.acc + 16 * J2;
     auto& reg = ctx->bases;
     if ((rc = ozl_rt_msm(ctx, reg[pk.h_h], pk.hc, n - 1, acc + 0 * J1))) return rc;
     if ((rc = ozl_rt_msm(ctx, reg[pk.h_l], pk.zc + (size_t)ni * 8, m - ni, acc + 1 * J1))) return rc;
@@ -291,43 +303,52 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     if ((rc = ozl_rt_msm(ctx, reg[pk.h_b2], pk.zc, m, acc_g2))) return rc;
 
     STAGE(ctx, "g16_assemble");
-    // scalars: rs[0]=r, rs[1]=s, rs[2]=1
+    // C = l + h + [s]alpha1 + [r]beta1 + [rs]delta1 + [s]a_acc + [r]b1_acc      (= l + h + sA + rB1 - rs delta1)
+    // A = alpha1 + a_acc + [r]delta1 ;  B = beta2 + b2_acc + [s]delta2
+    // scalars (8 words each) in pk.rs: [0]=r [1]=s [2]=1 [3]=rs ; lists from word 32*... below
     static const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
-    CUDA_TRY(ctx, cudaMemcpyAsync(pk.rs + 16, one, 32, cudaMemcpyHostToDevice, st));
-    uint32_t* sc = pk.rs + 32;            // scalar lists for lincomb
-    uint32_t* pts = acc + 4 * J1;         // G1 point lists (4 slots) ; results after
-    // A = alpha1 + a_acc + r delta1
+    uint32_t* S = pk.rs;                    // 16 scalars x 8 words
+    CUDA_TRY(ctx, cudaMemcpyAsync(S + 16, one, 32, cudaMemcpyHostToDevice, st));
+    f->mul_canonical(st, S + 0, S + 8, S + 24);
     auto cp = [&](uint32_t* dst, const uint32_t* src, size_t words) { return cudaMemcpyAsync(dst, src, words * 4, cudaMemcpyDeviceToDevice, st); };
-    CUDA_TRY(ctx, cp(pts + 0 * J1, pk.consts_g1 + 0 * J1, J1));
-    CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 2 * J1, J1));
-    CUDA_TRY(ctx, cp(pts + 2 * J1, pk.consts_g1 + 2 * J1, J1));
-    CUDA_TRY(ctx, cp(sc + 0, pk.rs + 16, 8));
-    CUDA_TRY(ctx, cp(sc + 8, pk.rs + 16, 8));
-    CUDA_TRY(ctx, cp(sc + 16, pk.rs + 0, 8));
-    uint32_t* A_jac = acc + 8 * J1;             // G1 results: slots 8, 9, 10
-    uint32_t* D_jac = A_jac + J1;
-    uint32_t* C_jac = D_jac + J1;
-    o1->lincomb(st, pts, sc, 3, A_jac);
-    // D = beta1 + b1_acc
-    CUDA_TRY(ctx, cp(pts + 0 * J1, pk.consts_g1 + 1 * J1, J1));
-    CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 3 * J1, J1));
-    o1->lincomb(st, pts, sc, 2, D_jac);
-    // C = l_acc + h_acc + s A + r D
-    CUDA_TRY(ctx, cp(pts + 0 * J1, acc + 1 * J1, J1));
-    CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 0 * J1, J1));
-    CUDA_TRY(ctx, cp(pts + 2 * J1, A_jac, J1));
-    CUDA_TRY(ctx, cp(pts + 3 * J1, D_jac, J1));
-    CUDA_TRY(ctx, cp(sc + 16, pk.rs + 8, 8));
-    CUDA_TRY(ctx, cp(sc + 24, pk.rs + 0, 8));
-    o1->lincomb(st, pts, sc, 4, C_jac);
-    // B = beta2 + b2_acc + s delta2   (G2)
-    uint32_t* pts2 = acc_g2 + J2;
+    // fixed-point terms (tables: alpha1, beta1, delta1, delta1) with scalars (s, r, rs, r)
+    uint32_t* fs = S + 32;                  // 4 scalars
+    CUDA_TRY(ctx, cp(fs + 0, S + 8, 8));
+    CUDA_TRY(ctx, cp(fs + 8, S + 0, 8));
+    CUDA_TRY(ctx, cp(fs + 16, S + 24, 8));
+    CUDA_TRY(ctx, cp(fs + 24, S + 0, 8));
+    uint32_t* fixed_out = acc + 12 * J1;    // 4 results: s*alpha1, r*beta1, rs*delta1, r*delta1
+    o1->scalar_mul_table(st, pk.tables_g1, fs, 4, fixed_out);
+    // variable-point terms: [s]a_acc, [r]b1_acc
+    uint32_t* vs = S + 64;                  // 2 scalars
+    CUDA_TRY(ctx, cp(vs + 0, S + 8, 8));
+    CUDA_TRY(ctx, cp(vs + 8, S + 0, 8));
+    uint32_t* var_out = acc + 16 * J1;      // 2 results
+    o1->scalar_mul_var(st, acc + 2 * J1, vs, 2, var_out);   // acc[2] = a_acc, acc[3] = b1_acc (adjacent)
+    // G2: [s]delta2
+    uint32_t* g2_fixed_out = acc_g2 + J2;
+    o2->scalar_mul_table(st, pk.tables_g2, S + 8, 1, g2_fixed_out);
+    // unit-scalar sums
+    uint32_t* ones = S + 80;                // 8 unit scalars
+    for (int i = 0; i < 8; i++) CUDA_TRY(ctx, cp(ones + 8 * i, S + 16, 8));
+    uint32_t* pts = acc + 20 * J1;          // up to 8 G1 points
+    uint32_t* A_jac = acc + 8 * J1;
+    uint32_t* C_jac = A_jac + J1;
+    CUDA_TRY(ctx, cp(pts + 0 * J1, pk.consts_g1 + 0 * J1, J1));   // alpha1
+    CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 2 * J1, J1));            // a_acc
+    CUDA_TRY(ctx, cp(pts + 2 * J1, fixed_out + 3 * J1, J1));      // r delta1
+    o1->lincomb(st, pts, ones, 3, A_jac);
+    CUDA_TRY(ctx, cp(pts + 0 * J1, acc + 1 * J1, J1));            // l_acc
+    CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 0 * J1, J1));            // h_acc
+    CUDA_TRY(ctx, cp(pts + 2 * J1, fixed_out, 3 * J1));           // s alpha1, r beta1, rs delta1
+    CUDA_TRY(ctx, cp(pts + 5 * J1, var_out, 2 * J1));             // s a_acc, r b1_acc
+    o1->lincomb(st, pts, ones, 7, C_jac);
+    uint32_t* pts2 = acc_g2 + 2 * J2;
     uint32_t* B_jac = pts2 + 3 * J2;
-    CUDA_TRY(ctx, cp(pts2 + 0 * J2, pk.consts_g2 + 0 * J2, J2));
-    CUDA_TRY(ctx, cp(pts2 + 1 * J2, acc_g2, J2));
-    CUDA_TRY(ctx, cp(pts2 + 2 * J2, pk.consts_g2 + 1 * J2, J2));
-    CUDA_TRY(ctx, cp(sc + 16, pk.rs + 8, 8));
-    o2->lincomb(st, pts2, sc, 3, B_jac);
+    CUDA_TRY(ctx, cp(pts2 + 0 * J2, pk.consts_g2 + 0 * J2, J2));  // beta2
+    CUDA_TRY(ctx, cp(pts2 + 1 * J2, acc_g2, J2));                 // b2_acc
+    CUDA_TRY(ctx, cp(pts2 + 2 * J2, g2_fixed_out, J2));           // s delta2
+    o2->lincomb(st, pts2, ones, 3, B_jac);
     // affine outputs
     if ((rc = ensure(ctx, ctx->out, 4096))) return rc;
     uint32_t* outb = (uint32_t*)ctx->out.p;
@@ -335,7 +356,7 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     o1->jacobian_to_affine(st, A_jac, outb, flags);
     o1->jacobian_to_affine(st, C_jac, outb + 2 * c1, flags + 1);
     o2->jacobian_to_affine(st, B_jac, outb + 4 * c1, flags + 2);
-    ctx->launches += 7;
+    ctx->launches += 10;
     STAGE_END(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(proof_a, outb, 2 * c1 * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(proof_c, outb + 2 * c1, 2 * c1 * 4, cudaMemcpyDeviceToHost, st));

@@ -25,8 +25,9 @@ namespace ozl {
 struct MsmPlan {
   int c;            // window width in bits
   int W;            // number of windows = ceil((scalar_bits + 1) / c)
+  int Wc;           // windows per precomputed copy (= W without precomputation); bucket sets = Wc
   uint32_t B;       // buckets per window = 2^(c-1)
-  uint32_t NB;      // W * B
+  uint32_t NB;      // Wc * B
   uint32_t L;       // sorted entries per accumulate slice (one thread each)
   uint32_t chunk;   // buckets per k_bucket_reduce thread
   uint32_t K;       // chunks per window = B / chunk
@@ -40,7 +41,7 @@ struct MsmPlan {
 // window-major array digits[w * n + i] (encoded bucket+1, sign in bit 31, 0 = no contribution) so
 // that the scatter can run window by window over contiguous 4-byte entries.
 static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t n,
-                               int c, int W, uint32_t B, uint32_t* __restrict__ counts, uint32_t* __restrict__ digits) {
+                               int c, int W, int Wc, uint32_t B, uint32_t* __restrict__ counts, uint32_t* __restrict__ digits) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const bool skip = inf_mask && ((inf_mask[i >> 3] >> (i & 7)) & 1);
     uint32_t s[8];
@@ -66,7 +67,7 @@ static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8
       }
       if (skip) v = 0;
       digits[(size_t)w * n + i] = v ? (v | (neg << 31)) : 0u;
-      if (v) atomicAdd(&counts[(uint32_t)w * B + (v - 1)], 1u);
+      if (v) atomicAdd(&counts[(uint32_t)(w % Wc) * B + (v - 1)], 1u);
     }
   }
 }
@@ -74,7 +75,8 @@ static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8
 // Counting-sort scatter of ONE window: the window's cursors (2^(c-1) words), offsets and the
 // 32-byte sectors being filled all stay L2-resident, so each sector of `sorted` reaches HBM once.
 static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, uint32_t n, uint32_t g_base,
-                                        const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
+                                        uint32_t idx_offset, const uint32_t* __restrict__ offsets,
+                                        uint32_t* __restrict__ cursor,
                                         uint32_t* __restrict__ sorted) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t d = digits_w[i];
@@ -82,7 +84,7 @@ static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, u
       const uint32_t g = g_base + (d & 0x7fffffffu) - 1u;
       // cursor[] enters holding the bucket's count; filling from the back leaves it zeroed
       const uint32_t pos = atomicSub(&cursor[g], 1u) - 1u;
-      sorted[offsets[g] + pos] = i | (d & 0x80000000u);
+      sorted[offsets[g] + pos] = (i + idx_offset) | (d & 0x80000000u);
     }
   }
 }
@@ -425,6 +427,46 @@ k_generate_bases(uint64_t start, uint32_t n, uint32_t* __restrict__ out) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// base precomputation: dst_i = 2^shift * src_i (affine in, affine out).  With copies at
+// 2^(c*Wc*q) the digits of window w = q*Wc + w' use copy q and bucket set w', so only Wc bucket
+// sets are reduced and the final Horner needs c*(Wc-1) doublings instead of c*(W-1).
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_precompute(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n, int shift) {
+  constexpr int AFF = 2 * F::N;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t first = (uint64_t)tid * GEN_RUN;
+  if (first >= n) return;
+  XYZZ<F> pts[GEN_RUN];
+  F pref[GEN_RUN];
+  F run = F::one();
+  const int m = (int)min((uint64_t)GEN_RUN, (uint64_t)n - first);
+  for (int i = 0; i < m; i++) {
+    Affine<F> a = load_affine<F>(src + (first + i) * AFF);
+    XYZZ<F> cur = (a.x.is_zero() && a.y.is_zero()) ? XYZZ<F>::identity() : XYZZ<F>::from_affine(a);
+    for (int k = 0; k < shift; k++) cur = cur.dbl();
+    pts[i] = cur;
+    pref[i] = run;
+    if (!cur.is_identity()) run = F::mul_ni(run, cur.zzz);
+  }
+  F inv = run.inverse();
+  for (int i = m - 1; i >= 0; i--) {
+    uint32_t* o = dst + (first + i) * AFF;
+    if (pts[i].is_identity()) {
+      F::zero().store(o);
+      F::zero().store(o + F::N);
+      continue;
+    }
+    F zi = F::mul_ni(inv, pref[i]);
+    inv = F::mul_ni(inv, pts[i].zzz);
+    F zi2 = F::sqr_ni(F::mul_ni(zi, pts[i].zz));
+    F::mul_ni(pts[i].x, zi2).store(o);
+    F::mul_ni(pts[i].y, zi).store(o + F::N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fixed-base scalar multiplication [k_j] G for a vector of scalars (known-trapdoor Groth16 setup:
 // ark_groth16::generate_parameters builds every query vector this way) -- plain double-and-add,
 // one thread per scalar, one inversion per thread for the affine output.  Setup path, not hot.
@@ -482,6 +524,65 @@ k_lincomb(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars
     F X, Y, Z;
     acc.to_jacobian(X, Y, Z);
     X.store(out_jac); Y.store(out_jac + F::N); Z.store(out_jac + 2 * F::N);
+  }
+}
+
+// Warp-parallel scalar multiplication for the proof assembly.  Block b (one warp) computes
+// s_b * P_b with the 256-bit scalar cut into 32 bytes: lane w multiplies T_w = 2^(8w) * P_b by
+// byte w (8 doublings + <= 8 additions) and the warp sums with a shuffle tree.  T comes either
+// from a table built once per fixed point (alpha, beta, delta of a proving key) or from a doubling
+// chain run by lane 0 (variable points: the MSM outputs) -- 248 doublings instead of the
+// 254 doublings + ~127 additions of plain double-and-add.
+template <class F, bool kUseTable>
+__global__ void __launch_bounds__(32)
+k_scalar_mul_warp(const uint32_t* __restrict__ pts_or_tables, const uint32_t* __restrict__ scalars, uint32_t* __restrict__ out_jac) {
+  constexpr int J = 3 * F::N;
+  __shared__ __align__(16) uint32_t tbl[32 * 4 * F::N];
+  const uint32_t b = blockIdx.x, lane = threadIdx.x;
+  XYZZ<F> T;
+  if (kUseTable) {
+    T = xyzz_from_jacobian<F>(pts_or_tables + ((size_t)b * 32 + lane) * J);
+  } else {
+    if (lane == 0) {
+      XYZZ<F> cur = xyzz_from_jacobian<F>(pts_or_tables + (size_t)b * J);
+      for (int w = 0; w < 32; w++) {
+        cur.store(tbl + w * 4 * F::N);
+        if (w < 31)
+          for (int k = 0; k < 8; k++) cur = cur.dbl();
+      }
+    }
+    __syncwarp();
+    T = XYZZ<F>::load(tbl + lane * 4 * F::N);
+  }
+  const uint32_t byte = (scalars[(size_t)b * 8 + (lane >> 2)] >> ((lane & 3) * 8)) & 0xffu;
+  XYZZ<F> acc = XYZZ<F>::identity();
+  for (int bit = 7; bit >= 0; bit--) {
+    acc = acc.dbl();
+    if ((byte >> bit) & 1) acc.add(T);
+  }
+  for (int d = 16; d >= 1; d >>= 1) {
+    XYZZ<F> o = shfl_down_xyzz(acc, d);
+    if (lane < (uint32_t)d) acc.add(o);
+  }
+  if (lane == 0) {
+    F X, Y, Z;
+    acc.to_jacobian(X, Y, Z);
+    X.store(out_jac + (size_t)b * J); Y.store(out_jac + (size_t)b * J + F::N); Z.store(out_jac + (size_t)b * J + 2 * F::N);
+  }
+}
+
+// table[w] = 2^(8w) * P for w < 32 (Jacobian), one thread; run once per fixed point
+template <class F>
+__global__ void k_build_byte_table(const uint32_t* __restrict__ pt_jac, uint32_t* __restrict__ table) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  constexpr int J = 3 * F::N;
+  XYZZ<F> cur = xyzz_from_jacobian<F>(pt_jac);
+  for (int w = 0; w < 32; w++) {
+    F X, Y, Z;
+    cur.to_jacobian(X, Y, Z);
+    X.store(table + (size_t)w * J); Y.store(table + (size_t)w * J + F::N); Z.store(table + (size_t)w * J + 2 * F::N);
+    if (w < 31)
+      for (int k = 0; k < 8; k++) cur = cur.dbl();
   }
 }
 

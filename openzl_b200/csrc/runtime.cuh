@@ -29,8 +29,10 @@ struct DevBuf {
 struct Bases {
   int curve = -1;
   size_t n = 0;
-  uint32_t* d_pts = nullptr;   // n * 2 * coord_u32
+  uint32_t* d_pts = nullptr;   // factor * n * 2 * coord_u32: copy q holds 2^(pc * pWc * q) * P_i
   uint8_t* d_inf = nullptr;    // optional bitset
+  int factor = 1;              // precomputed copies (ozl_msm_bases_precompute)
+  int pc = 0, pWc = 0;         // window bits / windows per copy fixed when the copies were built
 };
 
 struct Stage {
@@ -142,7 +144,7 @@ inline int coord_u32(int curve) {
 inline int scalar_bits(int curve) { return (curve == OZL_BLS12_381_G1 || curve == OZL_BLS12_381_G2) ? 255 : 254; }
 
 // Window width: minimise  W * (n * (1 + divergence) * madd + B * reduce)  in field multiplications.
-inline MsmPlan make_plan(int curve, size_t n, int forced_c) {
+inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0) {
   const int lambda = scalar_bits(curve);
   int best_c = 4;
   double best = 1e300;
@@ -161,7 +163,8 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c) {
   p.c = forced_c ? forced_c : best_c;
   p.W = (lambda + 1 + p.c - 1) / p.c;
   p.B = 1u << (p.c - 1);
-  p.NB = (uint32_t)p.W * p.B;
+  p.Wc = fixed_Wc ? fixed_Wc : p.W;
+  p.NB = (uint32_t)p.Wc * p.B;
   // slice length: 128 entries per thread when there is enough work to fill the chip, shorter otherwise
   {
     const uint64_t E = (uint64_t)n * p.W;
@@ -198,8 +201,8 @@ int run_scan(ozl_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out, Op op)
 template <class F>
 int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
   constexpr int XY = 4 * F::N;
-  const MsmPlan p = make_plan(b.curve, n, ctx->forced_c);
-  if ((uint64_t)n * p.W >= 0xffffffffull || n >= 0x7fffffffull) {
+  const MsmPlan p = b.factor > 1 ? make_plan(b.curve, n, b.pc, b.pWc) : make_plan(b.curve, n, ctx->forced_c);
+  if ((uint64_t)n * p.W >= 0xffffffffull || (uint64_t)b.n * b.factor >= 0x7fffffffull) {
     ctx->last_error = "msm: n too large for 32-bit indices";
     return OZL_ERR_ARG;
   }
@@ -209,8 +212,8 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   if ((r = ensure(ctx, ctx->sorted, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
   if ((r = ensure(ctx, ctx->digits, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
   if ((r = ensure(ctx, ctx->partials, (size_t)p.max_slots * XY * 4))) return r;
-  if ((r = ensure(ctx, ctx->chunk_out, (size_t)p.W * p.K * XY * 4))) return r;
-  if ((r = ensure(ctx, ctx->window_out, (size_t)p.W * XY * 4))) return r;
+  if ((r = ensure(ctx, ctx->chunk_out, (size_t)p.Wc * p.K * XY * 4))) return r;
+  if ((r = ensure(ctx, ctx->window_out, (size_t)p.Wc * XY * 4))) return r;
   if ((r = ensure(ctx, ctx->misc, 64))) return r;
 
   uint32_t* counts = (uint32_t*)ctx->counts.p;
@@ -227,7 +230,7 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   STAGE(ctx, "digits_count");
   CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)p.NB * 4, st));
   CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 64, st));
-  k_count<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.B, counts, digits);
+  k_count<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.Wc, p.B, counts, digits);
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
@@ -237,7 +240,8 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
 
   STAGE(ctx, "scatter");
   for (int w = 0; w < p.W && n; w++) {
-    k_scatter_window<<<grid_io, 256, 0, st>>>(digits + (size_t)w * n, (uint32_t)n, (uint32_t)w * p.B, offsets, counts, sorted);
+    k_scatter_window<<<grid_io, 256, 0, st>>>(digits + (size_t)w * n, (uint32_t)n, (uint32_t)(w % p.Wc) * p.B,
+                                             (uint32_t)((size_t)(w / p.Wc) * b.n), offsets, counts, sorted);
     LAUNCH_CHECK(ctx);
   }
   STAGE_END(ctx);
@@ -248,15 +252,15 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   STAGE_END(ctx);
 
   STAGE(ctx, "bucket_reduce");
-  const uint32_t total_chunks = (uint32_t)p.W * p.K;
+  const uint32_t total_chunks = (uint32_t)p.Wc * p.K;
   k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, offsets, p.L, total_chunks, p.K, p.B, p.chunk, chunk_out);
   LAUNCH_CHECK(ctx);
-  k_window_sum<F><<<p.W, 256, 0, st>>>(chunk_out, p.K, window_out);
+  k_window_sum<F><<<p.Wc, 256, 0, st>>>(chunk_out, p.K, window_out);
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
   STAGE(ctx, "final");
-  k_final<F><<<1, 32, 0, st>>>(window_out, p.W, p.c, d_out);
+  k_final<F><<<1, 32, 0, st>>>(window_out, p.Wc, p.c, d_out);
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
   return OZL_OK;

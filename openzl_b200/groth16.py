@@ -126,7 +126,8 @@ class Groth16:
     """Associated-function style like the reference's zero-sized ``Groth16<E>(PhantomData)``."""
 
     @staticmethod
-    def compile(ctx: Context, pairing: str, r1cs: R1CS, trapdoor: Trapdoor, keep_queries: bool = False):
+    def compile(ctx: Context, pairing: str, r1cs: R1CS, trapdoor: Trapdoor, keep_queries: bool = False,
+                precompute: int = 4):
         """Known-trapdoor circuit-specific setup -> (ProvingContext, VerifyingData)."""
         P = PAIRINGS[pairing]
         p = P["r"]
@@ -164,7 +165,8 @@ class Groth16:
 
         def upload(curve, scal):
             pts, inf = fixed_base_mul(ctx, curve, ints_to_limbs(scal))
-            return ctx.upload_bases(curve, pts, inf)
+            hb = ctx.upload_bases(curve, pts, inf)
+            return hb.precompute(precompute) if precompute > 1 else hb
 
         h_a, h_b1, h_b2 = upload(P["g1"], a), upload(P["g1"], b), upload(P["g2"], b)
         h_h, h_l = upload(P["g1"], hq), upload(P["g1"], lq)

@@ -174,6 +174,30 @@ def test_msm_known_dlog_large(ctx, log_n):
     assert (got == exp).all()
 
 
+@pytest.mark.parametrize("name,factor", [("bls12_381_g1", 2), ("bls12_381_g1", 4), ("bn254_g1", 3), ("bn254_g1", 8),
+                                         ("bn254_g2", 4), ("bls12_381_g2", 2)])
+def test_msm_precomputed_bases(ctx, name, factor):
+    """ozl_msm_bases_precompute keeps the result bit-identical (shifted copies, fewer bucket sets)."""
+    n = 3000 if name.endswith("g1") else 700
+    bases = cbind.bases_seq(name, 2, n)
+    scalars = directed_scalars(name, n, seed=factor)
+    inf = np.zeros((n + 7) // 8, dtype=np.uint8)
+    inf[3] = 0x10
+    exp, _ = oracle_affine(name, bases, scalars, inf=inf)
+    h = ctx.upload_bases(ozl.CURVE_IDS[name], bases, inf).precompute(factor)
+    try:
+        got, _ = gpu_affine(ctx, name, h.msm(scalars))
+        assert (got == exp).all()
+        # fewer scalars than bases on a precomputed handle (copies are strided by the handle's size)
+        m = n // 3
+        got2, _ = gpu_affine(ctx, name, h.msm(scalars[:m]))
+        exp2, _ = oracle_affine(name, bases[:m], scalars[:m], inf=inf[: (m + 7) // 8].copy() if False else inf)
+        assert (got2 == exp2).all()
+        assert (h.download(0, 8) == bases[:8]).all()
+    finally:
+        h.free()
+
+
 def test_reference_interface(ctx):
     """VariableBaseMSM::multi_scalar_mul mirror: size = min(len(bases), len(scalars))."""
     name = "bn254_g1"
