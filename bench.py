@@ -241,6 +241,7 @@ def run_ours(args):
         p1.record()
         torch.cuda.synchronize()
         value_plain = world * n / (p0.elapsed_time(p1) / 2 * 1e-3)
+        c_plain = ctx.window_bits(curve, n)
         tpre = time.perf_counter()
         bases.precompute(args.precompute)
         tpre = time.perf_counter() - tpre
@@ -322,9 +323,8 @@ def run_ours(args):
     acc = float(np.mean(stage_acc.get("accumulate", [float("nan")])))
     alg_bytes = n * 128.0
     achieved = alg_bytes / (acc * 1e-3) / 1e9
-    c = ctx.window_bits(curve, n)
-    W = (256 + c - 1) // c
-    Wc = (W + max(args.precompute, 1) - 1) // max(args.precompute, 1)
+    info = bases.info(n)
+    c, W, Wc = info["c"], info["windows"], info["bucket_sets"]
     mul_peak = ctx.bench_field_mul(0, 4000)
     madds_per_s = n * W / (acc * 1e-3)
     line = {

@@ -115,6 +115,9 @@ int ozl_msm_device_async(ozl_ctx* ctx, uint32_t handle, const uint64_t* d_scalar
 /* Pippenger window width in bits; 0 = choose from n (default). */
 int ozl_msm_set_window_bits(ozl_ctx* ctx, int c);
 int ozl_msm_get_window_bits(ozl_ctx* ctx, int curve, size_t n);
+/* The plan an n-scalar MSM on this handle will use: window bits, windows, bucket sets, copies. */
+int ozl_msm_bases_info(ozl_ctx* ctx, uint32_t handle, size_t n, int* c, int* windows, int* bucket_sets,
+                       int* factor);
 
 /* Sum k Jacobian points (host, X||Y||Z each) -- the combine step after the multi-GPU exchange
  * of per-rank partial sums (EC addition is not an NCCL reduction op). */

@@ -174,6 +174,13 @@ class Bases:
         self.ctx._check(self.ctx._lib.ozl_msm_bases_precompute(self.ctx._h, self.handle, factor), "ozl_msm_bases_precompute")
         return self
 
+    def info(self, n: Optional[int] = None) -> dict:
+        """Plan of an n-scalar MSM on this handle: window bits, windows, bucket sets, copies."""
+        v = [ctypes.c_int(0) for _ in range(4)]
+        self.ctx._check(self.ctx._lib.ozl_msm_bases_info(self.ctx._h, self.handle, self.n if n is None else n,
+                                                         *[ctypes.byref(x) for x in v]), "ozl_msm_bases_info")
+        return dict(c=v[0].value, windows=v[1].value, bucket_sets=v[2].value, factor=v[3].value)
+
     def download(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
         n = self.n - first if n is None else n
         out = np.zeros((n, 2 * self.coord_limbs), dtype=np.uint64)

@@ -217,7 +217,7 @@ int ozl_msm_bases_precompute(ozl_ctx* ctx, uint32_t handle, int factor) {
   if (factor == 1 || b->n == 0) return OZL_OK;
   if ((uint64_t)b->n * factor >= 0x7fffffffull) return OZL_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const MsmPlan p = make_plan(b->curve, b->n, ctx->forced_c);
+  const MsmPlan p = make_plan(b->curve, b->n, ctx->forced_c, 0, factor);
   const int Wc = (p.W + factor - 1) / factor;
   const int copies = (p.W + Wc - 1) / Wc;
   const size_t stride = (size_t)b->n * 2 * coord_u32(b->curve);
@@ -287,6 +287,19 @@ int ozl_msm_get_window_bits(ozl_ctx* ctx, int curve, size_t n) {
   return make_plan(curve, n, ctx->forced_c).c;
 }
 
+
+int ozl_msm_bases_info(ozl_ctx* ctx, uint32_t handle, size_t n, int* c, int* windows, int* bucket_sets, int* factor) {
+  if (!ctx) return OZL_ERR_ARG;
+  Bases* b;
+  int r = find_bases(ctx, handle, &b);
+  if (r) return r;
+  const MsmPlan p = b->factor > 1 ? make_plan(b->curve, n, b->pc, b->pWc) : make_plan(b->curve, n, ctx->forced_c);
+  if (c) *c = p.c;
+  if (windows) *windows = p.W;
+  if (bucket_sets) *bucket_sets = p.Wc;
+  if (factor) *factor = b->factor;
+  return OZL_OK;
+}
 
 int ozl_jacobian_sum(ozl_ctx* ctx, int curve, const uint64_t* points, size_t k, uint64_t* out_jacobian) {
   if (!ctx || !out_jacobian || (!points && k) || !coord_u32(curve)) return OZL_ERR_ARG;

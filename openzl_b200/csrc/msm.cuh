@@ -246,6 +246,71 @@ k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ so
   }
 }
 
+template <class F>
+__device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& a, int delta) {
+  XYZZ<F> r;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&a);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4 * F::N; i++) dst[i] = __shfl_down_sync(0xffffffffu, src[i], delta);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// heavy buckets.  A bucket that received very many points (skewed scalars, e.g. a witness full of
+// small values, or the short top window) spans many slices and therefore has many partials; summing
+// them inside one reduce thread would serialise.  Buckets with more than HEAVY_T partials are
+// collapsed here first: pass p treats the bucket's live partials (spaced 1024^p slots apart), one
+// warp sums a group of up to 1024 of them (32 per lane + shuffle tree) into the group's first slot.
+// After the passes the bucket's total sits in its first slot and k_bucket_reduce reads only that.
+// ---------------------------------------------------------------------------------------------
+static constexpr uint32_t HEAVY_T = 8;
+static constexpr uint32_t HEAVY_GROUP = 1024;
+static constexpr uint32_t HEAVY_GY = 16;
+
+template <class F>
+__global__ void __launch_bounds__(32)
+k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t NB, uint32_t L, uint32_t stride) {
+  constexpr int XY = 4 * F::N;
+  const uint32_t lane = threadIdx.x;
+  for (uint32_t g0 = blockIdx.x * 32; g0 < NB; g0 += gridDim.x * 32) {
+    const uint32_t g = g0 + lane;
+    uint32_t t0 = 0, nparts = 0;
+    if (g < NB) {
+      const uint32_t o0 = offsets[g], o1 = offsets[g + 1];
+      if (o1 > o0) {
+        t0 = o0 / L;
+        nparts = (o1 - 1) / L - t0 + 1;
+      }
+    }
+    const uint32_t live = (nparts + stride - 1) / stride;
+    uint32_t heavy = __ballot_sync(0xffffffffu, nparts > HEAVY_T && live > 1);
+    while (heavy) {
+      const int src = __ffs(heavy) - 1;
+      heavy &= heavy - 1;
+      const uint32_t hg = g0 + src;
+      const uint32_t ht0 = __shfl_sync(0xffffffffu, t0, src);
+      const uint32_t hlive = __shfl_sync(0xffffffffu, live, src);
+      const uint32_t ngroups = (hlive + HEAVY_GROUP - 1) / HEAVY_GROUP;
+      for (uint32_t q = blockIdx.y; q < ngroups; q += gridDim.y) {
+        const uint32_t j0 = q * HEAVY_GROUP;
+        const uint32_t j1 = min(j0 + HEAVY_GROUP, hlive);
+        XYZZ<F> acc = XYZZ<F>::identity();
+        for (uint32_t j = j0 + lane; j < j1; j += 32) {
+          XYZZ<F> pt = XYZZ<F>::load(partials + (size_t)(hg + ht0 + j * stride) * XY);
+          acc.add(pt);
+        }
+        for (int d = 16; d >= 1; d >>= 1) {
+          XYZZ<F> o = shfl_down_xyzz(acc, d);
+          if (lane < (uint32_t)d) acc.add(o);
+        }
+        if (lane == 0) acc.store(partials + (size_t)(hg + ht0 + j0 * stride) * XY);
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // bucket reduction: for a chunk of buckets [lo, lo + chunk) of window w computes
 //   sum_b (b + 1) * B_b   =   sum_b (b - lo + 1) B_b  +  lo * sum_b B_b
@@ -267,7 +332,9 @@ k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restric
     const uint32_t g = w * B + lo + j;
     const uint32_t o0 = offsets[g], o1 = offsets[g + 1];
     if (o1 > o0) {
-      const uint32_t t0 = o0 / L, t1 = (o1 - 1) / L;
+      const uint32_t t0 = o0 / L;
+      uint32_t t1 = (o1 - 1) / L;
+      if (t1 - t0 + 1 > HEAVY_T) t1 = t0;   // collapsed into its first slot by k_collapse_heavy
       for (uint32_t t = t0; t <= t1; t++) {
         XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + t) * XY);
         running.add(p);
@@ -280,16 +347,6 @@ k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restric
     acc.add(m);
   }
   acc.store(chunk_out + (size_t)gid * XY);
-}
-
-template <class F>
-__device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& a, int delta) {
-  XYZZ<F> r;
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(&a);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4 * F::N; i++) dst[i] = __shfl_down_sync(0xffffffffu, src[i], delta);
-  return r;
 }
 
 // One CTA per window: strided partial sums, then a warp-shuffle tree, then one more over warps.

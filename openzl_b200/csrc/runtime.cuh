@@ -143,17 +143,18 @@ inline int coord_u32(int curve) {
 }
 inline int scalar_bits(int curve) { return (curve == OZL_BLS12_381_G1 || curve == OZL_BLS12_381_G2) ? 255 : 254; }
 
-// Window width: minimise  W * (n * (1 + divergence) * madd + B * reduce)  in field multiplications.
-inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0) {
+// Window width: minimise field multiplications  n*W*10 (mixed adds) + 2*Wc*B*95 + (n*W/128)*45
+// (bucket reduction: two adds per bucket and one per slice partial, weighted by the efficiency
+// measured for the reduce kernels on B200: c=20 beats c=22 at 2^26, c=16 beats c=13 at 2^20), where Wc = ceil(W / factor) bucket sets remain after base precomputation.
+inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0, int factor = 1) {
   const int lambda = scalar_bits(curve);
   int best_c = 4;
   double best = 1e300;
-  for (int c = 4; c <= 22; c++) {
+  for (int c = 4; c <= 23; c++) {
     const int W = (lambda + 1 + c - 1) / c;
+    const int Wc = (W + factor - 1) / factor;
     const double B = std::ldexp(1.0, c - 1);
-    const double m = std::max((double)n / B, 1e-9);
-    const double diverge = 1.0 + 2.5 / std::sqrt(std::max(m, 1.0));
-    const double cost = W * ((double)n * diverge * 10.0 + B * 30.0);
+    const double cost = (double)n * W * 10.0 + 2.0 * Wc * B * 95.0 + ((double)n * W / 128.0) * 45.0;
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -252,6 +253,17 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   STAGE_END(ctx);
 
   STAGE(ctx, "bucket_reduce");
+  if (n) {
+    // heavy-bucket collapse: 3 passes cover 2^30 partials per bucket; no-ops when nothing is heavy
+    const dim3 hgrid((unsigned)std::min<uint32_t>((p.NB + 31) / 32, (uint32_t)ctx->sm_count * 16), HEAVY_GY);
+    uint32_t stride = 1;
+    for (int pass = 0; pass < 3; pass++) {
+      if ((uint64_t)n * p.W / p.L + 1 < stride) break;
+      k_collapse_heavy<F><<<hgrid, 32, 0, st>>>(partials, offsets, p.NB, p.L, stride);
+      LAUNCH_CHECK(ctx);
+      stride *= HEAVY_GROUP;
+    }
+  }
   const uint32_t total_chunks = (uint32_t)p.Wc * p.K;
   k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, offsets, p.L, total_chunks, p.K, p.B, p.chunk, chunk_out);
   LAUNCH_CHECK(ctx);

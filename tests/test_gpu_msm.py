@@ -125,6 +125,29 @@ def test_msm_all_zero_and_all_one_scalars(ctx):
         h.free()
 
 
+@pytest.mark.parametrize("c_bits", [12, 14])
+def test_msm_heavy_buckets(ctx, c_bits):
+    """Window widths whose top window has only 2-3 live bits put ~n/4 points in a few buckets;
+    with all-equal scalars every point of a window shares ONE bucket.  Both go through the
+    heavy-bucket collapse passes (more than 8 partials per bucket)."""
+    name = "bn254_g1"
+    n = 40000
+    r = curves.CURVES[name].fr.p
+    bases = cbind.bases_seq(name, 1, n)
+    h = ctx.upload_bases(ozl.BN254_G1, bases)
+    try:
+        ctx.set_window_bits(c_bits)
+        s1 = random_scalars(n, r, seed=c_bits)
+        got, _ = gpu_affine(ctx, name, h.msm(s1))
+        assert (got == oracle_affine(name, bases, s1)[0]).all()
+        s2 = np.tile(s1[:1], (n, 1))            # every scalar identical: one bucket per window
+        got, _ = gpu_affine(ctx, name, h.msm(s2))
+        assert (got == oracle_affine(name, bases, s2)[0]).all()
+    finally:
+        ctx.set_window_bits(0)
+        h.free()
+
+
 def test_msm_skewed_small_scalars(ctx):
     """Witness-like distribution: mostly 0/1/small values plus a few full-width ones."""
     name = "bn254_g1"
