@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include "fp.cuh"
 
 namespace ozl {
@@ -97,7 +98,7 @@ k_build_powers(const Fp<P>* __restrict__ base_p, const Fp<P>* __restrict__ scale
 //   post : 0 none | 1 multiply outputs by *scale | 2 multiply outputs by ghi[k>>lo]*glo[k&mask]
 //   last : write through the bit-reversal permutation (out must not alias in)
 template <class P, int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_ntt_pass(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ tw, int log_n, int s,
            int pre, int post, int last, const uint32_t* __restrict__ glo, const uint32_t* __restrict__ ghi,
            const Fp<P>* __restrict__ scale) {
@@ -212,11 +213,12 @@ int ntt_run(cudaStream_t st, NttWorkspace& ws, int field_id, uint32_t* d_data, u
     int post = 0;
     if (lastp && inverse) post = coset ? 2 : 1;
     const uint32_t threads = (uint32_t)(n >> R);
-    const uint32_t blocks = (threads + 255) / 256;
+    static const int kBlock = []() { const char* e = getenv("OZL_NTT_BLOCK"); int v = e ? atoi(e) : 128; return (v == 32 || v == 64 || v == 128) ? v : 128; }();
+    const uint32_t blocks = (threads + kBlock - 1) / kBlock;
     switch (R) {
-      case 1: k_ntt_pass<P, 1><<<blocks, 256, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
-      case 2: k_ntt_pass<P, 2><<<blocks, 256, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
-      default: k_ntt_pass<P, 3><<<blocks, 256, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
+      case 1: k_ntt_pass<P, 1><<<blocks, kBlock, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
+      case 2: k_ntt_pass<P, 2><<<blocks, kBlock, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
+      default: k_ntt_pass<P, 3><<<blocks, kBlock, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
     }
     (*launches)++;
     s += R;
