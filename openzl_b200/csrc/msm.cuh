@@ -67,7 +67,12 @@ static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8
       }
       if (skip) v = 0;
       digits[(size_t)w * n + i] = v ? (v | (neg << 31)) : 0u;
-      if (v) atomicAdd(&counts[(uint32_t)(w % Wc) * B + (v - 1)], 1u);
+      // warp-aggregated histogram update: lanes that hit the same bucket issue one atomic
+      // (keeps skewed inputs -- many equal scalars, short top window -- off the L2 same-address path)
+      const uint32_t active = __activemask();
+      const uint32_t peers = __match_any_sync(active, v);
+      if (v && (uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u))
+        atomicAdd(&counts[(uint32_t)(w % Wc) * B + (v - 1)], (uint32_t)__popc(peers));
     }
   }
 }
@@ -80,11 +85,20 @@ static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, u
                                         uint32_t* __restrict__ sorted) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t d = digits_w[i];
-    if (d) {
-      const uint32_t g = g_base + (d & 0x7fffffffu) - 1u;
+    const uint32_t key = d & 0x7fffffffu;
+    // warp-aggregated cursor update: one atomic per distinct bucket per warp
+    const uint32_t active = __activemask();
+    const uint32_t peers = __match_any_sync(active, key);
+    if (key) {
+      const uint32_t lane = threadIdx.x & 31u;
+      const int leader = __ffs(peers) - 1;
+      const uint32_t g = g_base + key - 1u;
+      uint32_t base = 0;
       // cursor[] enters holding the bucket's count; filling from the back leaves it zeroed
-      const uint32_t pos = atomicSub(&cursor[g], 1u) - 1u;
-      sorted[offsets[g] + pos] = (i + idx_offset) | (d & 0x80000000u);
+      if ((uint32_t)leader == lane) base = atomicSub(&cursor[g], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      sorted[offsets[g] + base - 1u - rank] = (i + idx_offset) | (d & 0x80000000u);
     }
   }
 }
