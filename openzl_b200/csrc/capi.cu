@@ -17,7 +17,7 @@ const OzlCurveOps* curve_ops(int curve) {
 int msm_dispatch(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
   const OzlCurveOps* ops = curve_ops(b.curve);
   if (!ops) return OZL_ERR_ARG;
-  return ops->msm(ctx, b, d_scalars, n, d_out);
+  return ops->msm(ctx, ctx->ws, ctx->stream, b, d_scalars, n, d_out);
 }
 
 int find_bases(ozl_ctx* ctx, uint32_t handle, Bases** out) {
@@ -96,8 +96,8 @@ void ozl_ctx_destroy(ozl_ctx* ctx) {
     cudaFree(kv.second.d_pts);
     if (kv.second.d_inf) cudaFree(kv.second.d_inf);
   }
-  DevBuf* bufs[] = {&ctx->scalars, &ctx->counts, &ctx->offsets, &ctx->tile_sums, &ctx->sorted, &ctx->digits,
-                    &ctx->partials, &ctx->chunk_out, &ctx->window_out, &ctx->misc, &ctx->out};
+  free_workspace(ctx->ws);
+  DevBuf* bufs[] = {&ctx->scalars, &ctx->out};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   NttWorkspace& nw = ctx->ntt_ws;

@@ -5,8 +5,9 @@
 namespace {
 typedef OZL_F F_;
 typedef OZL_C C_;
-int msm_entry(ozl_ctx* ctx, const ozl_rt::Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
-  return ozl_rt::msm_run<F_>(ctx, b, d_scalars, n, d_out);
+int msm_entry(ozl_ctx* ctx, ozl_rt::MsmWorkspace& ws, cudaStream_t st, const ozl_rt::Bases& b, const uint32_t* d_scalars,
+              size_t n, uint32_t* d_out) {
+  return ozl_rt::msm_run<F_>(ctx, ws, st, b, d_scalars, n, d_out);
 }
 void generate_entry(cudaStream_t st, uint64_t start, uint32_t n, uint32_t* d_pts) {
   const uint32_t threads = (n + GEN_RUN - 1) / GEN_RUN;

@@ -8,13 +8,15 @@
 struct ozl_ctx;
 namespace ozl_rt {
 struct Bases;
+struct MsmWorkspace;
 }
 namespace ozl {
 struct NttWorkspace;
 }
 
 struct OzlCurveOps {
-  int (*msm)(ozl_ctx* ctx, const ozl_rt::Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out);
+  int (*msm)(ozl_ctx* ctx, ozl_rt::MsmWorkspace& ws, cudaStream_t st, const ozl_rt::Bases& b, const uint32_t* d_scalars,
+             size_t n, uint32_t* d_out);
   void (*generate)(cudaStream_t st, uint64_t start, uint32_t n, uint32_t* d_pts);
   void (*jacobian_sum)(cudaStream_t st, const uint32_t* d_pts, uint32_t k, uint32_t* d_out);
   void (*jacobian_to_affine)(cudaStream_t st, const uint32_t* d_jac, uint32_t* d_out, int* d_flag);

@@ -32,6 +32,10 @@ struct Groth16Pk {
   uint32_t *z = nullptr, *zc = nullptr, *a = nullptr, *b = nullptr, *c = nullptr, *hc = nullptr;
   uint32_t *acc = nullptr;        // MSM outputs + assembly scratch
   uint32_t *rs = nullptr;         // scalars for the assembly
+  // the five MSMs run on three streams (main: h after the NTTs; s1: a, b1, l; s2: b2)
+  cudaStream_t s1 = nullptr, s2 = nullptr;
+  cudaEvent_t ev_z = nullptr, ev_s1 = nullptr, ev_s2 = nullptr;
+  MsmWorkspace ws1, ws2;
 };
 
 std::map<uint32_t, Groth16Pk>& pk_registry() {
@@ -76,6 +80,11 @@ void destroy_pk(ozl_ctx* ctx, Groth16Pk& pk) {
   void* ptrs[] = {pk.tables_g1, pk.tables_g2, pk.coef, pk.consts_g1, pk.consts_g2, pk.zinv, pk.z, pk.zc, pk.a, pk.b, pk.c, pk.hc, pk.acc, pk.rs};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (uint32_t h : {pk.h_a, pk.h_b1, pk.h_b2, pk.h_h, pk.h_l}) ozl_msm_bases_free(ctx, h);
+  free_workspace(pk.ws1);
+  free_workspace(pk.ws2);
+  if (pk.s1) cudaStreamDestroy(pk.s1);
+  if (pk.s2) cudaStreamDestroy(pk.s2);
+  for (cudaEvent_t e : {pk.ev_z, pk.ev_s1, pk.ev_s2}) if (e) cudaEventDestroy(e);
 }
 
 }  // namespace
@@ -212,6 +221,11 @@ int ozl_groth16_pk_create(ozl_ctx* ctx, int pairing, uint32_t n_constraints, uin
     g2_ops(pairing)->build_byte_table(ctx->stream, pk.consts_g2 + (size_t)1 * 3 * c2, pk.tables_g2);
     ctx->launches += 5;
   }
+  CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pk.s1, cudaStreamNonBlocking));
+  CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pk.s2, cudaStreamNonBlocking));
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_z, cudaEventDisableTiming));
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_s1, cudaEventDisableTiming));
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_s2, cudaEventDisableTiming));
   field_ops(fr_field(pairing))->vanishing_inv(ctx->stream, (int)log_n, pk.zinv);
   ctx->launches += 6;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -274,6 +288,21 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
   f->from_mont(st, pk.z, pk.zc, m);
   ctx->launches += 1;
   STAGE_END(ctx);
+  // the four MSMs over the assignment do not depend on the NTTs: start them on side streams now
+  uint32_t* const acc = pk.acc;
+  uint32_t* const acc_g2 = pk.acc + 16 * J2;
+  CUDA_TRY(ctx, cudaEventRecord(pk.ev_z, st));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(pk.s1, pk.ev_z, 0));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(pk.s2, pk.ev_z, 0));
+  {
+    auto& reg = ctx->bases;
+    if ((rc = ozl_rt_msm(ctx, pk.ws2, pk.s2, reg[pk.h_b2], pk.zc, m, acc_g2))) return rc;
+    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, reg[pk.h_a], pk.zc, m, acc + 2 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, reg[pk.h_b1], pk.zc, m, acc + 3 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, reg[pk.h_l], pk.zc + (size_t)ni * 8, m - ni, acc + 1 * J1))) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(pk.ev_s1, pk.s1));
+    CUDA_TRY(ctx, cudaEventRecord(pk.ev_s2, pk.s2));
+  }
 
   STAGE(ctx, "g16_ntt");
   int launches = 0;
@@ -293,14 +322,10 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
 
   {
     // MSM outputs (Jacobian): acc[0]=h, [1]=l, [2]=a, [3]=b1 in G1 slots; b2 in a G2 slot after them
-    uint32_t* acc = pk.acc;
-    uint32_t* acc_g2 = pk.acc + 16 * J2;
     auto& reg = ctx->bases;
-    if ((rc = ozl_rt_msm(ctx, reg[pk.h_h], pk.hc, n - 1, acc + 0 * J1))) return rc;
-    if ((rc = ozl_rt_msm(ctx, reg[pk.h_l], pk.zc + (size_t)ni * 8, m - ni, acc + 1 * J1))) return rc;
-    if ((rc = ozl_rt_msm(ctx, reg[pk.h_a], pk.zc, m, acc + 2 * J1))) return rc;
-    if ((rc = ozl_rt_msm(ctx, reg[pk.h_b1], pk.zc, m, acc + 3 * J1))) return rc;
-    if ((rc = ozl_rt_msm(ctx, reg[pk.h_b2], pk.zc, m, acc_g2))) return rc;
+    if ((rc = ozl_rt_msm(ctx, ctx->ws, st, reg[pk.h_h], pk.hc, n - 1, acc + 0 * J1))) return rc;
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, pk.ev_s1, 0));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, pk.ev_s2, 0));
 
     STAGE(ctx, "g16_assemble");
     // C = l + h + [s]alpha1 + [r]beta1 + [rs]delta1 + [s]a_acc + [r]b1_acc      (= l + h + sA + rB1 - rs delta1)

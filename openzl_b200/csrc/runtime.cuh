@@ -35,9 +35,16 @@ struct Bases {
   int pc = 0, pWc = 0;         // window bits / windows per copy fixed when the copies were built
 };
 
+// Scratch buffers of one MSM in flight.  The context owns one; the Groth16 prover owns two more so
+// that independent MSMs can run on separate streams and overlap their latency-bound tails.
+struct MsmWorkspace {
+  DevBuf counts, offsets, tile_sums, sorted, digits, partials, chunk_out, window_out, misc;
+};
+
 struct Stage {
   std::string name;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t stream = nullptr;
   int launches = 0;
 };
 
@@ -58,7 +65,8 @@ struct ozl_ctx {
   std::vector<Stage> stages;
   std::vector<Stage> event_pool;
   // workspace
-  DevBuf scalars, counts, offsets, tile_sums, sorted, digits, partials, chunk_out, window_out, misc, out;
+  DevBuf scalars, out;
+  MsmWorkspace ws;
   NttWorkspace ntt_ws;
 };
 
@@ -98,19 +106,20 @@ inline int ensure(ozl_ctx* ctx, DevBuf& b, size_t bytes) {
   return OZL_OK;
 }
 
-inline int stage_begin(ozl_ctx* ctx, const char* name) {
+inline int stage_begin(ozl_ctx* ctx, const char* name, cudaStream_t st = nullptr, bool use_st = false) {
   if (!ctx->timing) return OZL_OK;
   Stage s;
   s.name = name;
   CUDA_TRY(ctx, cudaEventCreate(&s.e0));
   CUDA_TRY(ctx, cudaEventCreate(&s.e1));
-  CUDA_TRY(ctx, cudaEventRecord(s.e0, ctx->stream));
+  s.stream = use_st ? st : ctx->stream;
+  CUDA_TRY(ctx, cudaEventRecord(s.e0, s.stream));
   ctx->stages.push_back(s);
   return OZL_OK;
 }
 inline int stage_end(ozl_ctx* ctx) {
   if (!ctx->timing) return OZL_OK;
-  CUDA_TRY(ctx, cudaEventRecord(ctx->stages.back().e1, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->stages.back().e1, ctx->stages.back().stream));
   return OZL_OK;
 }
 inline void stages_clear(ozl_ctx* ctx) {
@@ -124,6 +133,11 @@ inline void stages_clear(ozl_ctx* ctx) {
 #define STAGE(ctx, name)                          \
   do {                                            \
     int _r = stage_begin(ctx, name);              \
+    if (_r) return _r;                            \
+  } while (0)
+#define STAGE_ON(ctx, name, st)                   \
+  do {                                            \
+    int _r = stage_begin(ctx, name, st, true);    \
     if (_r) return _r;                            \
   } while (0)
 #define STAGE_END(ctx)                            \
@@ -190,22 +204,23 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0, in
 }
 
 template <class Op>
-int run_scan(ozl_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out, Op op) {
+int run_scan(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const uint32_t* in, uint32_t n, uint32_t* out, Op op) {
   const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  int r = ensure(ctx, ctx->tile_sums, (size_t)tiles * 4);
+  int r = ensure(ctx, ws.tile_sums, (size_t)tiles * 4);
   if (r) return r;
-  uint32_t* ts = (uint32_t*)ctx->tile_sums.p;
-  k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, ts, op);
+  uint32_t* ts = (uint32_t*)ws.tile_sums.p;
+  k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(in, n, ts, op);
   LAUNCH_CHECK(ctx);
-  k_scan_tile_offsets<<<1, 1024, 0, ctx->stream>>>(ts, tiles, out + n);
+  k_scan_tile_offsets<<<1, 1024, 0, st>>>(ts, tiles, out + n);
   LAUNCH_CHECK(ctx);
-  k_scan_apply<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, ts, out, op);
+  k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(in, n, ts, out, op);
   LAUNCH_CHECK(ctx);
   return OZL_OK;
 }
 
 template <class F>
-int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
+int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, const uint32_t* d_scalars, size_t n,
+            uint32_t* d_out) {
   constexpr int XY = 4 * F::N;
   const MsmPlan p = b.factor > 1 ? make_plan(b.curve, n, b.pc, b.pWc) : make_plan(b.curve, n, ctx->forced_c);
   if ((uint64_t)n * p.W >= 0xffffffffull || (uint64_t)b.n * b.factor >= 0x7fffffffull) {
@@ -213,38 +228,37 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
     return OZL_ERR_ARG;
   }
   int r;
-  if ((r = ensure(ctx, ctx->counts, (size_t)p.NB * 4))) return r;
-  if ((r = ensure(ctx, ctx->offsets, ((size_t)p.NB + 1) * 4))) return r;
-  if ((r = ensure(ctx, ctx->sorted, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
-  if ((r = ensure(ctx, ctx->digits, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
-  if ((r = ensure(ctx, ctx->partials, (size_t)p.max_slots * XY * 4))) return r;
-  if ((r = ensure(ctx, ctx->chunk_out, (size_t)p.Wc * p.K * XY * 4))) return r;
-  if ((r = ensure(ctx, ctx->window_out, (size_t)p.Wc * XY * 4))) return r;
-  if ((r = ensure(ctx, ctx->misc, 64))) return r;
+  if ((r = ensure(ctx, ws.counts, (size_t)p.NB * 4))) return r;
+  if ((r = ensure(ctx, ws.offsets, ((size_t)p.NB + 1) * 4))) return r;
+  if ((r = ensure(ctx, ws.sorted, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
+  if ((r = ensure(ctx, ws.digits, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
+  if ((r = ensure(ctx, ws.partials, (size_t)p.max_slots * XY * 4))) return r;
+  if ((r = ensure(ctx, ws.chunk_out, (size_t)p.Wc * p.K * XY * 4))) return r;
+  if ((r = ensure(ctx, ws.window_out, (size_t)p.Wc * XY * 4))) return r;
+  if ((r = ensure(ctx, ws.misc, 64))) return r;
 
-  uint32_t* counts = (uint32_t*)ctx->counts.p;
-  uint32_t* offsets = (uint32_t*)ctx->offsets.p;
-  uint32_t* sorted = (uint32_t*)ctx->sorted.p;
-  uint32_t* digits = (uint32_t*)ctx->digits.p;
-  uint32_t* partials = (uint32_t*)ctx->partials.p;
-  uint32_t* chunk_out = (uint32_t*)ctx->chunk_out.p;
-  uint32_t* window_out = (uint32_t*)ctx->window_out.p;
-  uint32_t* work_counter = (uint32_t*)ctx->misc.p;
-  cudaStream_t st = ctx->stream;
+  uint32_t* counts = (uint32_t*)ws.counts.p;
+  uint32_t* offsets = (uint32_t*)ws.offsets.p;
+  uint32_t* sorted = (uint32_t*)ws.sorted.p;
+  uint32_t* digits = (uint32_t*)ws.digits.p;
+  uint32_t* partials = (uint32_t*)ws.partials.p;
+  uint32_t* chunk_out = (uint32_t*)ws.chunk_out.p;
+  uint32_t* window_out = (uint32_t*)ws.window_out.p;
+  uint32_t* work_counter = (uint32_t*)ws.misc.p;
   const int grid_io = ctx->sm_count * 8;
 
-  STAGE(ctx, "digits_count");
+  STAGE_ON(ctx, "digits_count", st);
   CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)p.NB * 4, st));
   CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 64, st));
   k_count<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.Wc, p.B, counts, digits);
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
-  STAGE(ctx, "scan");
-  if ((r = run_scan(ctx, counts, p.NB, offsets, ScanIdentity{1}))) return r;
+  STAGE_ON(ctx, "scan", st);
+  if ((r = run_scan(ctx, ws, st, counts, p.NB, offsets, ScanIdentity{1}))) return r;
   STAGE_END(ctx);
 
-  STAGE(ctx, "scatter");
+  STAGE_ON(ctx, "scatter", st);
   for (int w = 0; w < p.W && n; w++) {
     k_scatter_window<<<grid_io, 256, 0, st>>>(digits + (size_t)w * n, (uint32_t)n, (uint32_t)(w % p.Wc) * p.B,
                                              (uint32_t)((size_t)(w / p.Wc) * b.n), offsets, counts, sorted);
@@ -252,12 +266,12 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   }
   STAGE_END(ctx);
 
-  STAGE(ctx, "accumulate");
+  STAGE_ON(ctx, "accumulate", st);
   k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, p.L, work_counter, partials);
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
-  STAGE(ctx, "bucket_reduce");
+  STAGE_ON(ctx, "bucket_reduce", st);
   if (n) {
     // heavy-bucket collapse: 3 passes cover 2^30 partials per bucket; no-ops when nothing is heavy
     const dim3 hgrid((unsigned)std::min<uint32_t>((p.NB + 31) / 32, (uint32_t)ctx->sm_count * 16), HEAVY_GY);
@@ -276,7 +290,7 @@ int msm_run(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, u
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
-  STAGE(ctx, "final");
+  STAGE_ON(ctx, "final", st);
   k_final<F><<<1, 32, 0, st>>>(window_out, p.Wc, p.c, d_out);
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
@@ -294,10 +308,17 @@ inline const OzlCurveOps* curve_ops_for(int curve) {
 }
 
 // MSM over the first n bases of b with device scalars / device output, enqueued on ctx->stream.
-inline int ozl_rt_msm(ozl_ctx* ctx, const Bases& b, const uint32_t* d_scalars, size_t n, uint32_t* d_out) {
+inline int ozl_rt_msm(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, const uint32_t* d_scalars, size_t n,
+                      uint32_t* d_out) {
   const OzlCurveOps* ops = curve_ops_for(b.curve);
   if (!ops || n > b.n) return OZL_ERR_ARG;
-  return ops->msm(ctx, b, d_scalars, n, d_out);
+  return ops->msm(ctx, ws, st, b, d_scalars, n, d_out);
+}
+
+inline void free_workspace(MsmWorkspace& ws) {
+  DevBuf* bufs[] = {&ws.counts, &ws.offsets, &ws.tile_sums, &ws.sorted, &ws.digits, &ws.partials, &ws.chunk_out, &ws.window_out, &ws.misc};
+  for (DevBuf* b : bufs)
+    if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
 }
 
 }  // namespace ozl_rt
