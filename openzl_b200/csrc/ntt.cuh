@@ -130,10 +130,14 @@ k_ntt_pass(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ui
     for (int m = 0; m < M; m++) {
       if (m & half) continue;
       const uint32_t e = (j0 + (uint32_t)(m & (half - 1)) * q) << (s + r);
-      const F w = F::load(tw + (size_t)e * F::N);
       const F a = x[m], b = x[m + half];
       x[m] = a + b;
-      x[m + half] = (a - b) * w;
+      if (e == 0) {
+        x[m + half] = a - b;   // unit twiddle: every butterfly of the final stage, half of the one before
+      } else {
+        const F w = F::load(tw + (size_t)e * F::N);
+        x[m + half] = (a - b) * w;
+      }
     }
   }
 #pragma unroll

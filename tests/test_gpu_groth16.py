@@ -90,6 +90,34 @@ def test_prove_matches_oracle_and_verifies(ctx, links):
         pk.free()
 
 
+def test_prove_bls12_381(ctx):
+    """Same prover on the other pairing family (`Pairing` for BLS12-381, pairing.rs:9-38): Poseidon
+    over BLS12-381 Fr with the width-3 / 8+55 rounds of the reference's tutorial KAT."""
+    from openzl_b200.circuits import PoseidonParams
+    pr = fields.BLS12_381_FR.p
+    ch = PoseidonChain(1, PoseidonParams.generate(modulus=pr))
+    # the chain's hash is the reference's permutation: KAT [3, 1, 2] from openzl-tutorials/src/poseidon.rs:388-401
+    assert ch.params.permute([3, 1, 2])[0] == 1808609226548932412441401219270714120272118151392880709881321306315053574086
+    r1 = ch.r1cs()
+    z = ch.assignment(42, 43)
+    assert r1.is_satisfied(z)
+    rnd = random.Random(381)
+    td = Trapdoor(*[rnd.randrange(2, pr) for _ in range(5)])
+    pk, vk = Groth16.compile(ctx, "bls12_381", r1, td)
+    try:
+        r, s = rnd.randrange(pr), rnd.randrange(pr)
+        proof, h_m = Groth16.prove_with_randomness(pk, ints_to_limbs(z, pr, mont=True), r, s, want_h=True)
+        h = og.witness_map("bls12_381_fr", r1, z)
+        assert limbs_to_ints(h_m, pr, mont=True) == h
+        A, B, C = og.prove_exponents("bls12_381_fr", r1, z, td, r, s, h=h)
+        assert og.verify_exponents("bls12_381_fr", r1, td, [z[1]], A, B, C)
+        for name, k, got in (("bls12_381_g1", A, proof.a), ("bls12_381_g2", B, proof.b), ("bls12_381_g1", C, proof.c)):
+            exp, exp_inf = cbind.to_affine(name, cbind.gen_mul(name, k))
+            assert not exp_inf and (got == exp).all(), name
+    finally:
+        pk.free()
+
+
 def test_prove_rejects_bad_shapes(ctx):
     ch = PoseidonChain(1)
     r1 = ch.r1cs()
