@@ -266,6 +266,85 @@ k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ so
   }
 }
 
+// Same kernel with the index stream staged through shared memory by the TMA engine: every lane
+// issues one 1-D bulk copy (cp.async.bulk, SASS UBLKCP) of the next TMA_CHUNK entries of its slice
+// into its row of the warp's staging tile, all 32 copies complete on one mbarrier, and the inner
+// loop reads indices from shared memory instead of issuing a dependent global load per point.
+static constexpr uint32_t TMA_CHUNK = 64;   // entries per lane per stage (256 B rows, 8 KB per warp)
+
+template <class F>
+__global__ void __launch_bounds__(128, (F::N <= 8 ? 4 : (F::N <= 12 ? 3 : 2)))
+k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                 uint32_t NB, uint32_t L, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials) {
+  constexpr int AFF = 2 * F::N;
+  constexpr int XY = 4 * F::N;
+  __shared__ __align__(128) uint32_t stage[4][32][TMA_CHUNK];
+  __shared__ __align__(8) uint64_t bars[4];
+  const uint32_t E = offsets[NB];
+  const uint32_t nslices = (E + L - 1) / L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t* bar = &bars[wid];
+  if (lane == 0) {
+    ptx::mbar_init(bar, 32);
+    ptx::mbar_fence_init();
+  }
+  __syncwarp();
+  uint32_t parity = 0;
+  uint32_t* row = &stage[wid][lane][0];
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(work_counter, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= nslices) break;
+    const uint32_t t = base + lane;
+    const bool live = t < nslices;
+    const uint32_t pos = live ? t * L : 0;
+    const uint32_t len = live ? min(L, E - pos) : 0;
+    uint32_t g = 0, boundary = 0;
+    if (live) {
+      uint32_t lo = 0, hi = NB;  // invariant: offsets[lo] <= pos < offsets[hi]
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= pos) lo = mid; else hi = mid;
+      }
+      g = lo;
+      boundary = offsets[g + 1];
+    }
+    XYZZ<F> acc = XYZZ<F>::identity();
+    const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
+    for (uint32_t done = 0; done < maxlen; done += TMA_CHUNK) {
+      const uint32_t my = len > done ? min(TMA_CHUNK, len - done) : 0;
+      const uint32_t bytes = (my * 4 + 15) & ~15u;
+      __syncwarp();                 // every lane has finished reading the previous stage
+      ptx::fence_proxy_async();     // order those generic-proxy reads before the async-proxy writes
+      if (bytes) {
+        ptx::mbar_arrive_expect_tx(bar, bytes);
+        ptx::tma_load_1d(row, sorted + pos + done, bytes, bar);
+      } else {
+        ptx::mbar_arrive(bar);
+      }
+      ptx::mbar_wait(bar, parity);
+      parity ^= 1;
+      for (uint32_t k = 0; k < my; k++) {
+        const uint32_t p = pos + done + k;
+        if (p == boundary) {
+          acc.store(partials + (size_t)(g + t) * XY);
+          acc = XYZZ<F>::identity();
+          do {
+            g++;
+            boundary = offsets[g + 1];
+          } while (boundary == p);
+        }
+        const uint32_t e = row[k];
+        Affine<F> pt = load_affine<F>(bases + (size_t)(e & 0x7fffffffu) * AFF);
+        pt.y = pt.y.cneg((e >> 31) != 0);
+        acc.add_mixed(pt);
+      }
+    }
+    if (live) acc.store(partials + (size_t)(g + t) * XY);
+  }
+}
+
 template <class F>
 __device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& a, int delta) {
   XYZZ<F> r;

@@ -70,6 +70,37 @@ OZL_DEV uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
 }
 
+// ---- TMA (cp.async.bulk) + mbarrier: stage contiguous global slices into shared memory ------
+OZL_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+OZL_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+OZL_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+OZL_DEV void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr(bar)) : "memory");
+}
+OZL_DEV void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+OZL_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (SASS: UBLKCP); bytes must be a multiple of 16, both addresses 16 B aligned
+OZL_DEV void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+OZL_DEV void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 #else  // ---- g++ emulation (tests only) ----------------------------------------------------
 
 static thread_local uint32_t g_cf = 0;

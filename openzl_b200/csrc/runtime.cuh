@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -191,7 +192,7 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0, in
     uint64_t L = E / ((uint64_t)148 * 384);
     if (L > 128) L = 128;
     if (L < 8) L = 8;
-    p.L = (uint32_t)L;
+    p.L = (uint32_t)L & ~7u;   // multiple of 8 entries: slices start 32-byte aligned (TMA needs 16)
   }
   uint32_t chunk = p.B / 4096;
   if (chunk < 4) chunk = 4;
@@ -267,7 +268,12 @@ int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, con
   STAGE_END(ctx);
 
   STAGE_ON(ctx, "accumulate", st);
-  k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, p.L, work_counter, partials);
+  {
+    // TMA-staged index stream by default; OZL_ACC_TMA=0 selects the plain global-load variant
+    static const bool use_tma = []() { const char* e = getenv("OZL_ACC_TMA"); return !(e && e[0] == '0'); }();
+    if (use_tma) k_accumulate_tma<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, p.L, work_counter, partials);
+    else k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, p.L, work_counter, partials);
+  }
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
