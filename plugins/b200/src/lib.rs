@@ -1,0 +1,121 @@
+//! FFI shim over `libozl_b200` (C ABI: `include/ozl.h`).
+//!
+//! UNCOMPILED in this repository (no Rust toolchain in the build image).  It mirrors, call for
+//! call, what `tests/test_gpu_msm.py` / `tests/test_gpu_ntt.py` do through ctypes, and replaces the
+//! two arkworks entry points `plugins/arkworks` re-exports:
+//!
+//! * `ark_ec::msm::VariableBaseMSM::multi_scalar_mul`  (`pub use ec`,   plugins/arkworks/src/lib.rs:28-29)
+//! * `ark_poly::EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place` (`pub use poly`, lib.rs:70-71)
+//!
+//! Memory conventions are arkworks' own: `Fp256/Fp384` hold Montgomery limbs (`fe.0.0`),
+//! `into_repr()` yields the canonical `BigInteger256` the MSM takes, so slices cross the boundary
+//! without conversion.  `GroupAffine` is not `repr(C)` (x, y, infinity + padding), hence the packing.
+
+use ark_ec::AffineCurve;
+use ark_ff::{BigInteger256, BigInteger384, PrimeField};
+use std::os::raw::c_int;
+
+#[repr(C)]
+pub struct OzlCtx {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    fn ozl_ctx_create(device: c_int, out: *mut *mut OzlCtx) -> c_int;
+    fn ozl_ctx_destroy(ctx: *mut OzlCtx);
+    fn ozl_msm_bases_upload(ctx: *mut OzlCtx, curve: c_int, bases: *const u64, inf_mask: *const u8, n: usize, handle: *mut u32) -> c_int;
+    fn ozl_msm_bases_precompute(ctx: *mut OzlCtx, handle: u32, factor: c_int) -> c_int;
+    fn ozl_msm_bases_free(ctx: *mut OzlCtx, handle: u32) -> c_int;
+    fn ozl_msm(ctx: *mut OzlCtx, handle: u32, scalars: *const u64, n: usize, out_jacobian: *mut u64) -> c_int;
+    fn ozl_ntt(ctx: *mut OzlCtx, field: c_int, data: *mut u64, log_n: u32, inverse: c_int, coset: c_int) -> c_int;
+}
+
+pub const OZL_BLS12_381_G1: c_int = 0;
+pub const OZL_BLS12_381_G2: c_int = 1;
+pub const OZL_BN254_G1: c_int = 2;
+pub const OZL_BN254_G2: c_int = 3;
+pub const OZL_BN254_FR: c_int = 0;
+pub const OZL_BLS12_381_FR: c_int = 1;
+
+/// Same opaque unit error as `plugins/arkworks/src/groth16.rs:35-45`.
+#[derive(Clone, Copy, Debug, Default, Eq, PartialEq)]
+pub struct Error;
+
+/// One context per (device, stream); not `Sync` (use one per thread).
+pub struct Context(*mut OzlCtx);
+
+impl Context {
+    pub fn new(device: i32) -> Result<Self, Error> {
+        let mut p = core::ptr::null_mut();
+        match unsafe { ozl_ctx_create(device, &mut p) } {
+            0 => Ok(Self(p)),
+            _ => Err(Error),
+        }
+    }
+}
+
+impl Drop for Context {
+    fn drop(&mut self) {
+        unsafe { ozl_ctx_destroy(self.0) }
+    }
+}
+
+/// Device-resident bases of one query vector of a proving key (`a_query`, `b_g1_query`, ...):
+/// they are constant across proofs (`ProvingContext<E>(pub ProvingKey<E>)`, groth16.rs:127-129).
+pub struct G1Bases381<'c> {
+    ctx: &'c Context,
+    handle: u32,
+    n: usize,
+}
+
+impl<'c> G1Bases381<'c> {
+    pub fn upload(ctx: &'c Context, bases: &[ark_bls12_381::G1Affine], precompute: i32) -> Result<Self, Error> {
+        let mut packed = Vec::<u64>::with_capacity(bases.len() * 12);
+        let mut inf = vec![0u8; (bases.len() + 7) / 8];
+        for (i, p) in bases.iter().enumerate() {
+            if p.is_zero() {
+                inf[i / 8] |= 1 << (i % 8);
+                packed.extend_from_slice(&[0u64; 12]);
+            } else {
+                packed.extend_from_slice(&p.x.0 .0); // Montgomery limbs, as stored
+                packed.extend_from_slice(&p.y.0 .0);
+            }
+        }
+        let mut handle = 0u32;
+        if unsafe { ozl_msm_bases_upload(ctx.0, OZL_BLS12_381_G1, packed.as_ptr(), inf.as_ptr(), bases.len(), &mut handle) } != 0 {
+            return Err(Error);
+        }
+        if precompute > 1 && unsafe { ozl_msm_bases_precompute(ctx.0, handle, precompute) } != 0 {
+            return Err(Error);
+        }
+        Ok(Self { ctx, handle, n: bases.len() })
+    }
+
+    /// Drop-in for `VariableBaseMSM::multi_scalar_mul(bases, scalars)`.
+    pub fn multi_scalar_mul(&self, scalars: &[<ark_bls12_381::Fr as PrimeField>::BigInt]) -> Result<ark_bls12_381::G1Projective, Error> {
+        let n = core::cmp::min(self.n, scalars.len()); // ark: size = min(bases.len(), scalars.len())
+        let mut out = [0u64; 18];
+        // BigInteger256 is a transparent [u64; 4]: the slice already is n x 4 canonical limbs
+        if unsafe { ozl_msm(self.ctx.0, self.handle, scalars.as_ptr() as *const u64, n, out.as_mut_ptr()) } != 0 {
+            return Err(Error);
+        }
+        let fq = |o: usize| ark_bls12_381::Fq::new(BigInteger384([out[o], out[o + 1], out[o + 2], out[o + 3], out[o + 4], out[o + 5]]));
+        Ok(ark_bls12_381::G1Projective::new(fq(0), fq(6), fq(12))) // Fp::new takes the Montgomery representation
+    }
+}
+
+impl Drop for G1Bases381<'_> {
+    fn drop(&mut self) {
+        unsafe { ozl_msm_bases_free(self.ctx.0, self.handle) };
+    }
+}
+
+/// Drop-in for `domain.{fft,ifft,coset_fft,coset_ifft}_in_place(&mut v)` with `v.len() == domain.size()`.
+pub fn ntt_in_place_bn254(ctx: &Context, v: &mut [ark_bn254::Fr], inverse: bool, coset: bool) -> Result<(), Error> {
+    debug_assert!(v.len().is_power_of_two());
+    let _: &BigInteger256 = &v[0].0; // layout check: Fp256 wraps BigInteger256([u64; 4])
+    match unsafe { ozl_ntt(ctx.0, OZL_BN254_FR, v.as_mut_ptr() as *mut u64, v.len().trailing_zeros(), inverse as c_int, coset as c_int) } {
+        0 => Ok(()),
+        _ => Err(Error),
+    }
+}
