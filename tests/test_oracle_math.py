@@ -36,6 +36,24 @@ def test_group_law_formulas(name):
     assert c.to_affine(c.add_mixed(c.identity_jac(), P)) == P
 
 
+def test_public_known_answer_doublings():
+    """Widely published doubling vectors (NOT from /root/reference, which holds no curve vectors):
+    2*G1 on BLS12-381 (zkcrypto/bls12_381 and the IETF pairing-friendly-curves draft) and
+    (1,2)+(1,2) on alt_bn128 (EIP-196 ecAdd test vector).  They pin the oracle's group law to
+    something outside this repository; the C++ oracle and the device are then compared with it."""
+    c = curves.BLS12_381_G1
+    assert c.mul_affine(c.gen, 2) == (
+        0x0572CBEA904D67468808C8EB50A9450C9721DB309128012543902D0AC358A62AE28F75BB8F1C7C42C39A8C5529BF0F4E,
+        0x166A9D8CABC673A322FDA673779D8E3822BA3ECB8670E461F73BB9021D5FD76A4C56D9D4CD16BD1BBA86881979749D28)
+    b = curves.BN254_G1
+    assert b.add_affine(b.gen, b.gen) == (
+        1368015179489954701390400359078579693043519447331113978918064868415326638035,
+        9918110051302171585080402603319702774565515993150576347155970296011118125764)
+    for name, cv in (("bls12_381_g1", c), ("bn254_g1", b)):
+        aff, inf = cbind.to_affine(name, cbind.gen_mul(name, 2))
+        assert not inf and cv.affine_from_mont_limbs(list(aff)) == cv.mul_affine(cv.gen, 2)
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_msm_ark_equals_naive_and_dlog(name):
     c = curves.CURVES[name]
