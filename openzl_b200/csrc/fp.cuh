@@ -193,6 +193,90 @@ struct Fp {
 
   OZL_DEV Fp sqr() const { return *this * *this; }
 
+  // ---- Montgomery squaring (separated operand scanning) --------------------------------------
+  // Separated operand scanning: t = a^2 as 2 * (off-diagonal products) + diagonal, then N
+  // reduction rows.  N(N-1)/2 + N + N^2 wide multiplies instead of 2 N^2 (222 vs 288 for N = 12);
+  // the extra work is carry bookkeeping on the otherwise idle ALU pipe.
+  //
+  // Off-diagonal row i adds a_i * a_j (j > i) at limb i + j.  The products with j - i odd and those
+  // with j - i even each form one carry chain over disjoint limb pairs.  The chain that stops one
+  // limb lower runs first; its carry lands in limb i + N, which so far holds at most a carry bit,
+  // and the carry of the second chain lands in limb i + N + 1, which is still zero.
+  //
+  // Measured on B200 inside k_accumulate: neutral for 8 limbs and 9 % SLOWER for 12 limbs (the 2N-limb
+  // intermediate costs registers and the carry bookkeeping lengthens the dependent chains), so the hot
+  // path keeps sqr() = mul(); this variant stays available and tested (tests/test_host_emu.py).
+  OZL_DEV Fp sqr_sos() const {
+    const uint32_t* a = v;
+    uint32_t t[2 * N];
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) t[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) {
+      // chain "x": j = i+1, i+3, ... ; chain "y": j = i+2, i+4, ...   (N even: x reaches j = N-1 iff i even)
+      const int lower_start = (i % 2 == 0) ? i + 2 : i + 1;
+      const int higher_start = (i % 2 == 0) ? i + 1 : i + 2;
+#pragma unroll
+      for (int pass = 0; pass < 2; pass++) {
+        const int j0 = pass == 0 ? lower_start : higher_start;
+        if (j0 < N) {
+          int last = j0;
+#pragma unroll
+          for (int j = j0; j < N; j += 2) {
+            const int s = i + j;
+            t[s] = (j == j0) ? ptx::mad_lo_cc(a[i], a[j], t[s]) : ptx::madc_lo_cc(a[i], a[j], t[s]);
+            t[s + 1] = ptx::madc_hi_cc(a[i], a[j], t[s + 1]);
+            last = s + 1;
+          }
+          t[last + 1] = ptx::addc(t[last + 1], 0);
+        }
+      }
+    }
+    // t = 2 t  (2 T < a^2 < 2^(64N): no carry out)
+    t[0] = ptx::add_cc(t[0], t[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * N - 1; k++) t[k] = ptx::addc_cc(t[k], t[k]);
+    t[2 * N - 1] = ptx::addc(t[2 * N - 1], t[2 * N - 1]);
+    // t += sum a_i^2 2^(64 i)
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      t[2 * i] = (i == 0) ? ptx::mad_lo_cc(a[i], a[i], t[2 * i]) : ptx::madc_lo_cc(a[i], a[i], t[2 * i]);
+      t[2 * i + 1] = (i == N - 1) ? ptx::madc_hi(a[i], a[i], t[2 * i + 1]) : ptx::madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+    }
+    // Montgomery reduction: row i clears limb i.  Carries out of a chain target limbs >= N, which never
+    // feed a later multiplier m, so they are parked in cr[] (cr[k] -> limb N + k) and added once at the end.
+    uint32_t cr[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; k++) cr[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const uint32_t m = ptx::mul_lo(t[i], P::INV);
+      t[i] = ptx::mad_lo_cc(P::mod()[0], m, t[i]);
+      t[i + 1] = ptx::madc_hi_cc(P::mod()[0], m, t[i + 1]);
+#pragma unroll
+      for (int j = 2; j < N; j += 2) {
+        t[i + j] = ptx::madc_lo_cc(P::mod()[j], m, t[i + j]);
+        t[i + j + 1] = ptx::madc_hi_cc(P::mod()[j], m, t[i + j + 1]);
+      }
+      cr[i] = ptx::addc(cr[i], 0);          // even chain stops at limb i + N - 1
+      t[i + 1] = ptx::mad_lo_cc(P::mod()[1], m, t[i + 1]);
+      t[i + 2] = ptx::madc_hi_cc(P::mod()[1], m, t[i + 2]);
+#pragma unroll
+      for (int j = 3; j < N; j += 2) {
+        t[i + j] = ptx::madc_lo_cc(P::mod()[j], m, t[i + j]);
+        t[i + j + 1] = ptx::madc_hi_cc(P::mod()[j], m, t[i + j + 1]);
+      }
+      cr[i + 1] = ptx::addc(cr[i + 1], 0);  // odd chain stops at limb i + N
+    }
+    Fp r;
+    r.v[0] = ptx::add_cc(t[N], cr[0]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) r.v[k] = ptx::addc_cc(t[N + k], cr[k]);
+    r.v[N - 1] = ptx::addc(t[2 * N - 1], cr[N - 1]);
+    final_sub(r.v);
+    return r;
+  }
+
   // Out-of-line multiplier for the cold kernels: one ~5 KB copy instead of a ~6 KB inlined body
   // per call site, so bucket reduction / Horner / inversion stay resident in the instruction cache
   // (ncu: sm__icc_request_hit_rate 50 % -> the inlined versions were instruction-fetch bound).
@@ -298,6 +382,7 @@ struct Fp2 {
     r.c1 = m.dbl();
     return r;
   }
+  OZL_DEV Fp2 sqr_sos() const { return sqr(); }   // (test hook symmetry with Fp)
   // complex squaring: 2 base multiplications
   OZL_DEV Fp2 sqr() const {
     Base s = c0 + c1;

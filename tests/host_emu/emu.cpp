@@ -20,6 +20,7 @@ static void fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 4: r = x.inverse(); break;
     case 5: r = x.sqr(); break;
     case 6: r = x.dbl(); break;
+    case 7: r = x.sqr_sos(); break;
     default: r = F::zero();
   }
   memcpy(out, &r, sizeof(F));
