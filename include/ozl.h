@@ -109,6 +109,12 @@ int ozl_msm_bases_free(ozl_ctx* ctx, uint32_t handle);
  * like ark's `size = min(bases.len(), scalars.len())`).  Host scalars in, host Jacobian out. */
 int ozl_msm(ozl_ctx* ctx, uint32_t handle, const uint64_t* scalars, size_t n,
             uint64_t* out_jacobian);
+/* Pipelined form of ozl_msm for back-to-back MSMs (a prover streaming proofs): returns as soon as
+ * the work is enqueued.  Scalars are copied on a separate copy stream into one of two staging
+ * buffers, so the host->device transfer of call i+1 overlaps the kernels of call i.  `scalars`
+ * and `out_jacobian` must stay valid (and should be page-locked) until ozl_ctx_synchronize. */
+int ozl_msm_submit(ozl_ctx* ctx, uint32_t handle, const uint64_t* scalars, size_t n,
+                   uint64_t* out_jacobian);
 /* Device scalars in, device Jacobian out; enqueued on the context's stream, not synchronized. */
 int ozl_msm_device_async(ozl_ctx* ctx, uint32_t handle, const uint64_t* d_scalars, size_t n,
                          uint64_t* d_out_jacobian);

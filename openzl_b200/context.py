@@ -201,6 +201,10 @@ class Bases:
     def msm_host_ptr(self, scalars_ptr: int, n: int, out: np.ndarray) -> None:
         self.ctx._check(self.ctx._lib.ozl_msm(self.ctx._h, self.handle, scalars_ptr, n, _ptr(out)), "ozl_msm")
 
+    def msm_submit(self, scalars_ptr: int, n: int, out_ptr: int) -> None:
+        """Pipelined host-buffer MSM (returns after enqueueing; `Context.synchronize()` completes it)."""
+        self.ctx._check(self.ctx._lib.ozl_msm_submit(self.ctx._h, self.handle, scalars_ptr, n, out_ptr), "ozl_msm_submit")
+
     def msm_device(self, d_scalars: int, n: int, d_out: int) -> None:
         """Device pointers in/out; asynchronous on the context's stream."""
         self.ctx._check(self.ctx._lib.ozl_msm_device_async(self.ctx._h, self.handle, d_scalars, n, d_out),

@@ -97,6 +97,13 @@ void ozl_ctx_destroy(ozl_ctx* ctx) {
     if (kv.second.d_inf) cudaFree(kv.second.d_inf);
   }
   free_workspace(ctx->ws);
+  for (int k = 0; k < 2; k++) {
+    if (ctx->pipe_scalars[k].p) cudaFree(ctx->pipe_scalars[k].p);
+    if (ctx->pipe_out[k].p) cudaFree(ctx->pipe_out[k].p);
+    if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
+    if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
+  }
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   DevBuf* bufs[] = {&ctx->scalars, &ctx->out};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -124,6 +131,7 @@ void* ozl_ctx_get_stream(ozl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullp
 
 int ozl_ctx_synchronize(ozl_ctx* ctx) {
   if (!ctx) return OZL_ERR_ARG;
+  if (ctx->copy_stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return OZL_OK;
 }
@@ -273,6 +281,36 @@ int ozl_msm(ozl_ctx* ctx, uint32_t handle, const uint64_t* scalars, size_t n, ui
   if ((r = msm_dispatch(ctx, *b, (const uint32_t*)ctx->scalars.p, n, (uint32_t*)ctx->out.p))) return r;
   CUDA_TRY(ctx, cudaMemcpyAsync(out_jacobian, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OZL_OK;
+}
+
+int ozl_msm_submit(ozl_ctx* ctx, uint32_t handle, const uint64_t* scalars, size_t n, uint64_t* out_jacobian) {
+  if (!ctx || !out_jacobian || (!scalars && n)) return OZL_ERR_ARG;
+  Bases* b;
+  int r = find_bases(ctx, handle, &b);
+  if (r) return r;
+  if (n > b->n) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
+    }
+  }
+  const int k = (int)(ctx->pipe_idx++ & 1u);
+  const size_t out_bytes = 3 * coord_u32(b->curve) * 4;
+  // the staging buffer may still feed the MSM submitted two calls ago
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k], 0));
+  if ((r = ensure(ctx, ctx->pipe_scalars[k], std::max<size_t>(n, 1) * 32))) return r;
+  if ((r = ensure(ctx, ctx->pipe_out[k], 1024))) return r;
+  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pipe_scalars[k].p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_h2d[k], ctx->copy_stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[k], 0));
+  if (ctx->timing) stages_clear(ctx);
+  if ((r = msm_dispatch(ctx, *b, (const uint32_t*)ctx->pipe_scalars[k].p, n, (uint32_t*)ctx->pipe_out[k].p))) return r;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_jacobian, ctx->pipe_out[k].p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_done[k], ctx->stream));
   return OZL_OK;
 }
 

@@ -68,6 +68,11 @@ struct ozl_ctx {
   // workspace
   DevBuf scalars, out;
   MsmWorkspace ws;
+  // double-buffered host->device pipeline of ozl_msm_submit
+  cudaStream_t copy_stream = nullptr;
+  DevBuf pipe_scalars[2], pipe_out[2];
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  unsigned pipe_idx = 0;
   NttWorkspace ntt_ws;
 };
 

@@ -232,6 +232,26 @@ def test_reference_interface(ctx):
     assert not inf and (got == exp).all()
 
 
+def test_msm_submit_pipeline(ctx):
+    """ozl_msm_submit: three back-to-back submissions with different scalars, one synchronize."""
+    name = "bn254_g1"
+    n = 5000
+    r = curves.CURVES[name].fr.p
+    bases = cbind.bases_seq(name, 1, n)
+    h = ctx.upload_bases(ozl.BN254_G1, bases)
+    try:
+        scal = [random_scalars(n, r, seed=100 + i) for i in range(3)]
+        outs = [np.zeros(12, dtype=np.uint64) for _ in range(3)]
+        for s, o in zip(scal, outs):
+            h.msm_submit(s.ctypes.data, n, o.ctypes.data)
+        ctx.synchronize()
+        for s, o in zip(scal, outs):
+            got, _ = gpu_affine(ctx, name, o)
+            assert (got == oracle_affine(name, bases, s)[0]).all()
+    finally:
+        h.free()
+
+
 def test_jacobian_sum(ctx):
     name = "bls12_381_g1"
     ks = [5, 7, 0, 11]
