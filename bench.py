@@ -201,6 +201,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     n = 1 << args.log_n
+    if args.total_log_n:
+        # strong scaling (BASELINE config 5): a fixed 2^total_log_n-point MSM split by point range
+        assert (1 << args.total_log_n) % world == 0
+        n = (1 << args.total_log_n) // world
     curve = ozl.BLS12_381_G1
 
     ctx = ozl.Context(local_rank)
@@ -353,9 +357,9 @@ def run_ours(args):
     madds_per_s = n * W / (acc * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.total_log_n else "weak", "vs_baseline": None,
         "dtype": "u32 limbs (Montgomery, 381-bit)", "data": "synthetic",
-        "config": {"workload": f"BLS12-381 G1 Pippenger MSM, 2^{args.log_n} points per GPU, window c={c} ({W} windows in {Wc} bucket sets, signed digits)",
+        "config": {"workload": f"BLS12-381 G1 Pippenger MSM, {n} points per GPU ({world * n} total), window c={c} ({W} windows in {Wc} bucket sets, signed digits)",
                    "bases": "P_i=[start+i]G generated on device, resident (constant across steps like a proving key)",
                    "precompute_factor": args.precompute, "precompute_s": (tpre if args.precompute > 1 else 0.0),
                    "value_without_precompute": value_plain,
@@ -525,6 +529,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=26)
+    ap.add_argument("--total-log-n", type=int, default=0, help="strong scaling: total points = 2^k split across ranks")
     ap.add_argument("--cpu-log-n", type=int, default=20)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--precompute", type=int, default=4, help="shifted base copies kept in HBM (1 = none)")

@@ -197,6 +197,8 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0, in
     uint64_t L = E / ((uint64_t)148 * 384);
     if (L > 128) L = 128;
     if (L < 8) L = 8;
+    static const int kForceL = []() { const char* e = getenv("OZL_MSM_L"); return e ? atoi(e) : 0; }();
+    if (kForceL >= 8) L = (uint64_t)kForceL;
     p.L = (uint32_t)L & ~7u;   // multiple of 8 entries: slices start 32-byte aligned (TMA needs 16)
   }
   uint32_t chunk = p.B / 4096;
