@@ -444,16 +444,19 @@ k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restric
   acc.store(chunk_out + (size_t)gid * XY);
 }
 
-// One CTA per window: strided partial sums, then a warp-shuffle tree, then one more over warps.
+// Sum of the chunk results of each bucket set in two launches: block (w, y) adds every Y-th chunk
+// result of set w (strided partial sums, a warp-shuffle tree, then one more tree over the warps) and
+// writes one point; the second launch (Y = 1) folds those Y points.  One block per set alone would
+// be a 3.9 ms latency chain at K = 32768.
 template <class F>
 __global__ void __launch_bounds__(256)
-k_window_sum(const uint32_t* __restrict__ chunk_out, uint32_t K, uint32_t* __restrict__ window_out) {
+k_window_sum(const uint32_t* __restrict__ in, uint32_t K, uint32_t* __restrict__ out) {
   constexpr int XY = 4 * F::N;
   __shared__ __align__(16) uint32_t warp_res[8 * XY];
-  const uint32_t w = blockIdx.x;
+  const uint32_t w = blockIdx.x, y = blockIdx.y, Y = gridDim.y;
   XYZZ<F> acc = XYZZ<F>::identity();
-  for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) {
-    XYZZ<F> p = XYZZ<F>::load(chunk_out + ((size_t)w * K + k) * XY);
+  for (uint32_t k = y + threadIdx.x * Y; k < K; k += blockDim.x * Y) {
+    XYZZ<F> p = XYZZ<F>::load(in + ((size_t)w * K + k) * XY);
     acc.add(p);
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -469,7 +472,7 @@ k_window_sum(const uint32_t* __restrict__ chunk_out, uint32_t K, uint32_t* __res
       XYZZ<F> o = shfl_down_xyzz(a, d);
       if (lane < d) a.add(o);
     }
-    if (lane == 0) a.store(window_out + (size_t)w * XY);
+    if (lane == 0) a.store(out + ((size_t)w * Y + y) * XY);
   }
 }
 

@@ -241,7 +241,7 @@ int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, con
   if ((r = ensure(ctx, ws.sorted, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
   if ((r = ensure(ctx, ws.digits, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
   if ((r = ensure(ctx, ws.partials, (size_t)p.max_slots * XY * 4))) return r;
-  if ((r = ensure(ctx, ws.chunk_out, (size_t)p.Wc * p.K * XY * 4))) return r;
+  if ((r = ensure(ctx, ws.chunk_out, ((size_t)p.Wc * p.K + (size_t)p.Wc * 64) * XY * 4))) return r;
   if ((r = ensure(ctx, ws.window_out, (size_t)p.Wc * XY * 4))) return r;
   if ((r = ensure(ctx, ws.misc, 64))) return r;
 
@@ -299,8 +299,18 @@ int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, con
   const uint32_t total_chunks = (uint32_t)p.Wc * p.K;
   k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, offsets, p.L, total_chunks, p.K, p.B, p.chunk, chunk_out);
   LAUNCH_CHECK(ctx);
-  k_window_sum<F><<<p.Wc, 256, 0, st>>>(chunk_out, p.K, window_out);
-  LAUNCH_CHECK(ctx);
+  {
+    const uint32_t Y = p.K >= 4096 ? 64 : 1;          // fan-out of the first summation launch
+    uint32_t* stage = chunk_out + (size_t)p.Wc * p.K * XY;   // Y points per set, after the chunk results
+    if (Y > 1) {
+      k_window_sum<F><<<dim3(p.Wc, Y), 256, 0, st>>>(chunk_out, p.K, stage);
+      LAUNCH_CHECK(ctx);
+      k_window_sum<F><<<dim3(p.Wc, 1), 256, 0, st>>>(stage, Y, window_out);
+    } else {
+      k_window_sum<F><<<dim3(p.Wc, 1), 256, 0, st>>>(chunk_out, p.K, window_out);
+    }
+    LAUNCH_CHECK(ctx);
+  }
   STAGE_END(ctx);
 
   STAGE_ON(ctx, "final", st);
