@@ -6,6 +6,8 @@ Host-side mirror of the reference's surface (same names and argument meaning):
 
 * ``openzl_b200.ec.VariableBaseMSM.multi_scalar_mul(bases, scalars)``  -- ark_ec::msm, via `pub use ec`
 * ``openzl_b200.poly.Radix2EvaluationDomain`` / ``GeneralEvaluationDomain`` -- ark_poly, via `pub use poly`
+* ``openzl_b200.groth16.Groth16.{compile, prove}`` -- the plugin's ``ProofSystem`` impl (groth16.rs:399-467)
+* ``openzl_b200.serialize`` -- ark ``CanonicalSerialize`` bytes of ``Proof`` / ``ProvingKey`` (groth16.rs:98-179)
 
 Importing this package never touches ``oracle/`` and there is no CPU fallback: constructing a
 ``Context`` without ``libozl_b200.so`` or without a CUDA device raises.
@@ -13,9 +15,9 @@ Importing this package never touches ``oracle/`` and there is no CPU fallback: c
 from ._lib import (BLS12_381_FR, BLS12_381_G1, BLS12_381_G2, BN254_FR, BN254_G1, BN254_G2, CURVE_IDS, FIELD_IDS,
                    OzlError, OzlLibraryError)
 from .context import Bases, Context
-from . import ec, poly
+from . import ec, poly, serialize
 
-__all__ = ["Context", "Bases", "OzlError", "OzlLibraryError", "ec", "poly", "BLS12_381_G1", "BLS12_381_G2", "BN254_G1",
+__all__ = ["Context", "Bases", "OzlError", "OzlLibraryError", "ec", "poly", "serialize", "BLS12_381_G1", "BLS12_381_G2", "BN254_G1",
            "BN254_G2", "BN254_FR", "BLS12_381_FR", "CURVE_IDS", "FIELD_IDS", "default_context"]
 
 _default_ctx = None

@@ -86,6 +86,11 @@ class Proof:
     b: np.ndarray   # G2 affine
     c: np.ndarray   # G1 affine
 
+    def to_bytes(self, pairing: str) -> bytes:
+        """``proof_as_bytes`` (groth16.rs:98-107): ark's compressed a || b || c."""
+        from . import serialize
+        return serialize.proof_limbs_as_bytes(pairing, self.a, self.b, self.c)
+
 
 class ProvingContext:
     """``ProvingContext<E>(ProvingKey<E>)`` resident on the device."""
