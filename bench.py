@@ -213,6 +213,16 @@ def run_ours(args):
 
     ctx = ozl.Context(local_rank)
     ctx.use_torch_stream()
+    # --precompute 0 = measured best on B200: from 2^25 points a full set of shifted copies (one
+    # bucket set, c = 22: 12 windows, 72 GiB of bases at 2^26) beats 4 copies at c = 20 by 5 %
+    # (profiles/msm_sweep_c_r01.jsonl); below that 4 copies with the planner's window.
+    pre_window = 0
+    if args.precompute == 0:
+        max_copies = int(80e9 // (n * 96))           # keep the copies under ~80 GB of the 180 GB
+        if n >= (1 << 25) and max_copies >= 12 and not args.window_bits:
+            args.precompute, pre_window = 12, 22
+        else:
+            args.precompute = max(1, min(4, max_copies))
     if args.window_bits:
         ctx.set_window_bits(args.window_bits)
     start = 1 + rank * n
@@ -251,7 +261,10 @@ def run_ours(args):
         value_plain = world * n / (p0.elapsed_time(p1) / 2 * 1e-3)
         c_plain = ctx.window_bits(curve, n)
         tpre = time.perf_counter()
+        if pre_window:
+            ctx.set_window_bits(pre_window)      # the copies are built for this window width
         bases.precompute(args.precompute)
+        ctx.synchronize()
         tpre = time.perf_counter() - tpre
     for _ in range(args.warmup):
         step()
@@ -563,7 +576,7 @@ def main():
     ap.add_argument("--total-log-n", type=int, default=0, help="strong scaling: total points = 2^k split across ranks")
     ap.add_argument("--cpu-log-n", type=int, default=20)
     ap.add_argument("--window-bits", type=int, default=0)
-    ap.add_argument("--precompute", type=int, default=4, help="shifted base copies kept in HBM (1 = none)")
+    ap.add_argument("--precompute", type=int, default=0, help="shifted base copies kept in HBM (1 = none, 0 = best measured for the size)")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

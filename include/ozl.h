@@ -121,6 +121,11 @@ int ozl_msm_device_async(ozl_ctx* ctx, uint32_t handle, const uint64_t* d_scalar
 /* Pippenger window width in bits; 0 = choose from n (default). */
 int ozl_msm_set_window_bits(ozl_ctx* ctx, int c);
 int ozl_msm_get_window_bits(ozl_ctx* ctx, int curve, size_t n);
+/* EXPERIMENTAL: run the first `levels` halving levels of bucket accumulation with batched-affine
+ * additions (one shared inversion per thread, msm_batch.cuh) before the XYZZ accumulation.
+ * 0 = off, -1 = library default (off; measured no faster than XYZZ on B200).
+ * The result is the same group element either way. */
+int ozl_msm_set_batch_affine(ozl_ctx* ctx, int levels);
 /* The plan an n-scalar MSM on this handle will use: window bits, windows, bucket sets, copies. */
 int ozl_msm_bases_info(ozl_ctx* ctx, uint32_t handle, size_t n, int* c, int* windows, int* bucket_sets,
                        int* factor);

@@ -26,7 +26,7 @@ EXPORTS = [
     "ozl_version", "ozl_strerror", "ozl_last_error", "ozl_ctx_create", "ozl_ctx_destroy", "ozl_ctx_set_stream", "ozl_ctx_use_own_stream",
     "ozl_ctx_get_stream", "ozl_ctx_synchronize", "ozl_curve_coord_limbs", "ozl_msm_bases_upload",
     "ozl_msm_bases_upload_device", "ozl_msm_bases_generate", "ozl_msm_bases_precompute", "ozl_msm_bases_download", "ozl_msm_bases_free",
-    "ozl_msm", "ozl_msm_submit", "ozl_msm_device_async", "ozl_msm_set_window_bits", "ozl_msm_get_window_bits", "ozl_msm_bases_info", "ozl_jacobian_sum",
+    "ozl_msm", "ozl_msm_submit", "ozl_msm_device_async", "ozl_msm_set_window_bits", "ozl_msm_set_batch_affine", "ozl_msm_get_window_bits", "ozl_msm_bases_info", "ozl_jacobian_sum",
     "ozl_jacobian_to_affine", "ozl_ntt", "ozl_ntt_device_async", "ozl_ctx_enable_timing",
     "ozl_ctx_get_stage_times", "ozl_ctx_launch_count", "ozl_bench_field_mul", "ozl_fr_spmv", "ozl_fixed_base_mul",
     "ozl_groth16_pk_create", "ozl_groth16_pk_destroy", "ozl_groth16_prove", "ozl_groth16_domain_size",
@@ -95,6 +95,7 @@ def load() -> ctypes.CDLL:
     lib.ozl_msm_submit.argtypes = [vp, ctypes.c_uint32, vp, sz, vp]
     lib.ozl_msm_device_async.argtypes = [vp, ctypes.c_uint32, vp, sz, vp]
     lib.ozl_msm_set_window_bits.argtypes = [vp, ctypes.c_int]
+    lib.ozl_msm_set_batch_affine.argtypes = [vp, ctypes.c_int]
     lib.ozl_msm_get_window_bits.argtypes = [vp, ctypes.c_int, sz]
     ip = ctypes.POINTER(ctypes.c_int)
     lib.ozl_msm_bases_info.argtypes = [vp, ctypes.c_uint32, sz, ip, ip, ip, ip]

@@ -93,6 +93,10 @@ class Context:
     def set_window_bits(self, c: int):
         self._check(self._lib.ozl_msm_set_window_bits(self._h, c), "ozl_msm_set_window_bits")
 
+    def set_batch_affine(self, levels: int):
+        """EXPERIMENTAL batched-affine pair levels before the XYZZ accumulation (0 = off, -1 = default)."""
+        self._check(self._lib.ozl_msm_set_batch_affine(self._h, levels), "ozl_msm_set_batch_affine")
+
     def window_bits(self, curve: int, n: int) -> int:
         return int(self._lib.ozl_msm_get_window_bits(self._h, curve, n))
 

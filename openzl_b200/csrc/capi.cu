@@ -320,6 +320,12 @@ int ozl_msm_set_window_bits(ozl_ctx* ctx, int c) {
   return OZL_OK;
 }
 
+int ozl_msm_set_batch_affine(ozl_ctx* ctx, int levels) {
+  if (!ctx || levels < -1 || levels > 8) return OZL_ERR_ARG;
+  ctx->batch_levels = levels;
+  return OZL_OK;
+}
+
 int ozl_msm_get_window_bits(ozl_ctx* ctx, int curve, size_t n) {
   if (!ctx || !coord_u32(curve)) return -1;
   return make_plan(curve, n, ctx->forced_c).c;

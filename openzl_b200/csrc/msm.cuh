@@ -216,7 +216,9 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const 
 // ---------------------------------------------------------------------------------------------
 // Resident CTAs per SM, measured on B200: BN254 G1 (8 limbs) gains 7 % from 4 CTAs (124 registers, no
 // spills); BLS12-381 G1 (12 limbs) loses 5 % when squeezed to 128 registers, so it stays at 3 (168).
-template <class F>
+// DIRECT: the entries ARE the points (output of the batched-affine pair levels, msm_batch.cuh):
+// entry p is point p, no sign, and (0, 0) encodes a pair that cancelled to the identity.
+template <class F, bool DIRECT = false>
 __global__ void __launch_bounds__(128, (F::N <= 8 ? 4 : (F::N <= 12 ? 3 : 2)))
 k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
              uint32_t NB, uint32_t L, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials) {
@@ -252,9 +254,13 @@ k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ so
             boundary = offsets[g + 1];
           } while (boundary == p);
         }
-        const uint32_t e = sorted[p];
+        const uint32_t e = DIRECT ? p : sorted[p];
         Affine<F> pt = load_affine<F>(bases + (size_t)(e & 0x7fffffffu) * AFF);
-        pt.y = pt.y.cneg((e >> 31) != 0);
+        if (DIRECT) {
+          if (pt.x.is_zero() && pt.y.is_zero()) continue;
+        } else {
+          pt.y = pt.y.cneg((e >> 31) != 0);
+        }
         acc.add_mixed(pt);   // inlined multiplier: an out-of-line one costs +26 % here (measured)
       }
       acc.store(partials + (size_t)(g + t) * XY);

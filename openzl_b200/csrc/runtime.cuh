@@ -14,6 +14,7 @@
 #include "../../include/ozl.h"
 #include "params_gen.cuh"
 #include "msm.cuh"
+#include "msm_batch.cuh"
 #include "ntt.cuh"
 #include "curve_ops.h"
 
@@ -40,6 +41,9 @@ struct Bases {
 // that independent MSMs can run on separate streams and overlap their latency-bound tails.
 struct MsmWorkspace {
   DevBuf counts, offsets, tile_sums, sorted, digits, partials, chunk_out, window_out, misc;
+  // batched-affine pair levels (msm_batch.cuh): per-level offsets, chunk table, ping-pong point
+  // buffers, prefix-product scratch, and the last level's point lists
+  DevBuf lvl_off, pair_tab, pair_a, pair_b, pair_pre, lvl_pts;
 };
 
 struct Stage {
@@ -61,6 +65,7 @@ struct ozl_ctx {
   std::map<uint32_t, Bases> bases;
   uint32_t next_handle = 1;
   int forced_c = 0;
+  int batch_levels = -1;   // batched-affine pair levels: -1 = environment default (off), 0 = off, 1..8
   uint64_t launches = 0;
   bool timing = false;
   std::vector<Stage> stages;
@@ -226,6 +231,97 @@ int run_scan(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const uint32_t* in
   return OZL_OK;
 }
 
+// ---- batched-affine pair levels (kernels in msm_batch.cuh) ----------------------------------
+struct BatchConfig {
+  int levels;             // halving levels before the XYZZ accumulation (0 = off)
+  uint32_t k;             // target additions per thread (one inversion each)
+  uint64_t min_entries;   // below this many sorted entries the plain path is used
+  double scratch_gb;      // bound on the per-chunk ping-pong + prefix scratch
+};
+inline BatchConfig batch_config() {
+  static const BatchConfig cfg = []() {
+    BatchConfig c{0, 1024, 1ull << 22, 12.0};
+    if (const char* e = getenv("OZL_MSM_BATCH")) c.levels = atoi(e);
+    if (const char* e = getenv("OZL_MSM_BATCH_K")) c.k = (uint32_t)atoi(e);
+    if (const char* e = getenv("OZL_MSM_BATCH_MIN")) c.min_entries = strtoull(e, nullptr, 10);
+    if (const char* e = getenv("OZL_MSM_BATCH_GB")) c.scratch_gb = atof(e);
+    if (c.levels < 0) c.levels = 0;
+    if (c.levels > 8) c.levels = 8;
+    if (c.k < 16) c.k = 16;
+    return c;
+  }();
+  return cfg;
+}
+
+template <class F>
+int run_pair_levels(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, const MsmPlan& p, const BatchConfig& bc,
+                    int T, size_t n, const uint32_t* sorted, const uint32_t* offsets, const uint32_t* lvl_off) {
+  constexpr int AFF = 2 * F::N;
+  int r;
+  // chunks of about equal entry counts so that the level buffers fit the scratch budget
+  const double E_bound = (double)n * p.W;
+  const double bytes_per_entry = 0.5 * (AFF * 4 + F::N * 4) + 0.25 * AFF * 4;   // level-1 out + prefixes + level-2 out
+  uint32_t Q = (uint32_t)std::ceil(E_bound * bytes_per_entry / (bc.scratch_gb * 1e9));
+  if (Q < 1) Q = 1;
+  if (Q > 4096) Q = 4096;
+  const size_t tab_words = (size_t)(T + 2) * (Q + 1);
+  if ((r = ensure(ctx, ws.pair_tab, tab_words * 4))) return r;
+  uint32_t* d_tab = (uint32_t*)ws.pair_tab.p;
+  k_pair_chunk_table<<<(Q + 1 + 127) / 128, 128, 0, st>>>(offsets, lvl_off, p.NB, Q, (uint32_t)T, d_tab);
+  LAUNCH_CHECK(ctx);
+  std::vector<uint32_t> tab(tab_words);
+  CUDA_TRY(ctx, cudaMemcpyAsync(tab.data(), d_tab, tab_words * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  auto off_at = [&](int l, uint32_t q) { return tab[(size_t)(1 + l) * (Q + 1) + q]; };
+
+  // buffer sizes from the actual chunk extents
+  size_t max_l1 = 0, max_l2 = 0;
+  for (uint32_t q = 0; q < Q; q++) {
+    max_l1 = std::max<size_t>(max_l1, off_at(1, q + 1) - off_at(1, q));
+    if (T >= 2) max_l2 = std::max<size_t>(max_l2, off_at(2, q + 1) - off_at(2, q));
+  }
+  const size_t E_T = off_at(T, Q);
+  // odd levels write buffer a, even levels buffer b; the last level writes lvl_pts
+  const size_t a_entries = T >= 2 ? max_l1 : 0, b_entries = T >= 3 ? max_l2 : 0;
+  if ((r = ensure(ctx, ws.pair_a, std::max<size_t>(a_entries, 1) * AFF * 4))) return r;
+  if ((r = ensure(ctx, ws.pair_b, std::max<size_t>(b_entries, 1) * AFF * 4))) return r;
+  if ((r = ensure(ctx, ws.lvl_pts, std::max<size_t>(E_T, 1) * AFF * 4))) return r;
+  const int per_sm = (F::N <= 8 ? 4 : (F::N <= 12 ? 3 : 2)) * 128;
+  const size_t resident = (size_t)ctx->sm_count * per_sm;
+  // prefix scratch: k * T_total elements; T_total < n_out / k + 129 and k <= max(bc.k, 16) (see the k choice below)
+  if ((r = ensure(ctx, ws.pair_pre, (max_l1 + (size_t)129 * std::max<uint32_t>(bc.k, 16) + 128) * F::N * 4))) return r;
+  uint32_t* lvl_pts = (uint32_t*)ws.lvl_pts.p;
+  uint32_t* pre = (uint32_t*)ws.pair_pre.p;
+
+  for (uint32_t q = 0; q < Q; q++) {
+    const uint32_t g_lo = tab[q], g_hi = tab[q + 1];
+    if (g_hi == g_lo) continue;
+    for (int l = 1; l <= T; l++) {
+      const uint32_t o_begin = off_at(l, q), o_end = off_at(l, q + 1);
+      if (o_end == o_begin) continue;
+      const uint32_t n_out = o_end - o_begin;
+      // additions per thread: whole waves of uniformly loaded threads, about bc.k each
+      uint32_t waves = (uint32_t)((n_out + (uint64_t)bc.k * resident - 1) / ((uint64_t)bc.k * resident));
+      uint32_t k = (uint32_t)((n_out + (uint64_t)waves * resident - 1) / ((uint64_t)waves * resident));
+      if (k < 16) k = 16;
+      const uint32_t nvt = (n_out + k - 1) / k;
+      const uint32_t grid = (nvt + 127) / 128;
+      const uint32_t* off_in = l == 1 ? offsets : lvl_off + (size_t)(l - 2) * (p.NB + 1);
+      const uint32_t* off_out = lvl_off + (size_t)(l - 1) * (p.NB + 1);
+      const uint32_t* src = l == 1 ? b.d_pts : (const uint32_t*)((l & 1) ? ws.pair_b.p : ws.pair_a.p);
+      uint32_t* dst = l == T ? lvl_pts : (uint32_t*)((l & 1) ? ws.pair_a.p : ws.pair_b.p);
+      const uint32_t dst_base = l == T ? 0u : o_begin;
+      const uint32_t in_base = off_at(l - 1, q);
+      if (l == 1)
+        k_pair_level<F, true><<<grid, 128, 0, st>>>(src, sorted, off_in, off_out, g_lo, g_hi, o_begin, o_end, in_base, dst_base, k, pre, dst);
+      else
+        k_pair_level<F, false><<<grid, 128, 0, st>>>(src, sorted, off_in, off_out, g_lo, g_hi, o_begin, o_end, in_base, dst_base, k, pre, dst);
+      LAUNCH_CHECK(ctx);
+    }
+  }
+  return OZL_OK;
+}
+
 template <class F>
 int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, const uint32_t* d_scalars, size_t n,
             uint32_t* d_out) {
@@ -262,8 +358,24 @@ int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, con
   LAUNCH_CHECK(ctx);
   STAGE_END(ctx);
 
+  // Batched-affine pair levels (msm_batch.cuh): T halving levels before the XYZZ accumulation.
+  BatchConfig bc = batch_config();
+  if (ctx->batch_levels >= 0) {      // explicit request: honoured at every size
+    bc.levels = ctx->batch_levels;
+    bc.min_entries = 0;
+  }
+  const int T = (n && (uint64_t)n * p.W >= bc.min_entries) ? bc.levels : 0;
+  uint32_t* lvl_off = nullptr;
+  if (T) {
+    if ((r = ensure(ctx, ws.lvl_off, (size_t)T * ((size_t)p.NB + 1) * 4))) return r;
+    lvl_off = (uint32_t*)ws.lvl_off.p;
+  }
+
   STAGE_ON(ctx, "scan", st);
   if ((r = run_scan(ctx, ws, st, counts, p.NB, offsets, ScanIdentity{1}))) return r;
+  // level-l lists hold ceil(count / 2^l) entries per bucket (counts are consumed by the scatter below)
+  for (int l = 1; l <= T; l++)
+    if ((r = run_scan(ctx, ws, st, counts, p.NB, lvl_off + (size_t)(l - 1) * (p.NB + 1), ScanCeilDiv{1u << l}))) return r;
   STAGE_END(ctx);
 
   STAGE_ON(ctx, "scatter", st);
@@ -274,8 +386,26 @@ int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, con
   }
   STAGE_END(ctx);
 
+  const uint32_t* acc_offsets = offsets;   // offsets of the lists the XYZZ accumulation walks
+  uint32_t acc_L = p.L;
+  if (T) {
+    STAGE_ON(ctx, "pair_levels", st);
+    if ((r = run_pair_levels<F>(ctx, ws, st, b, p, bc, T, n, sorted, offsets, lvl_off))) return r;
+    STAGE_END(ctx);
+    acc_offsets = lvl_off + (size_t)(T - 1) * (p.NB + 1);
+    uint64_t L = (((uint64_t)n * p.W) >> T) / ((uint64_t)148 * 384);
+    if (L > 128) L = 128;
+    if (L < 8) L = 8;
+    acc_L = (uint32_t)L & ~7u;
+    const size_t slots = (size_t)p.NB + ((((size_t)n * p.W) >> T) + p.NB) / acc_L + 2;
+    if ((r = ensure(ctx, ws.partials, slots * XY * 4))) return r;
+    partials = (uint32_t*)ws.partials.p;
+  }
+
   STAGE_ON(ctx, "accumulate", st);
-  {
+  if (T) {
+    k_accumulate<F, true><<<ctx->sm_count * 4, 128, 0, st>>>((const uint32_t*)ws.lvl_pts.p, nullptr, acc_offsets, p.NB, acc_L, work_counter, partials);
+  } else {
     // TMA-staged index stream by default; OZL_ACC_TMA=0 selects the plain global-load variant
     static const bool use_tma = []() { const char* e = getenv("OZL_ACC_TMA"); return !(e && e[0] == '0'); }();
     if (use_tma) k_accumulate_tma<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, p.L, work_counter, partials);
@@ -290,14 +420,14 @@ int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, con
     const dim3 hgrid((unsigned)std::min<uint32_t>((p.NB + 31) / 32, (uint32_t)ctx->sm_count * 16), HEAVY_GY);
     uint32_t stride = 1;
     for (int pass = 0; pass < 3; pass++) {
-      if ((uint64_t)n * p.W / p.L + 1 < stride) break;
-      k_collapse_heavy<F><<<hgrid, 32, 0, st>>>(partials, offsets, p.NB, p.L, stride);
+      if ((uint64_t)n * p.W / acc_L + 1 < stride) break;
+      k_collapse_heavy<F><<<hgrid, 32, 0, st>>>(partials, acc_offsets, p.NB, acc_L, stride);
       LAUNCH_CHECK(ctx);
       stride *= HEAVY_GROUP;
     }
   }
   const uint32_t total_chunks = (uint32_t)p.Wc * p.K;
-  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, offsets, p.L, total_chunks, p.K, p.B, p.chunk, chunk_out);
+  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, acc_offsets, acc_L, total_chunks, p.K, p.B, p.chunk, chunk_out);
   LAUNCH_CHECK(ctx);
   {
     const uint32_t Y = p.K >= 4096 ? 64 : 1;          // fan-out of the first summation launch
@@ -339,7 +469,8 @@ inline int ozl_rt_msm(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bas
 }
 
 inline void free_workspace(MsmWorkspace& ws) {
-  DevBuf* bufs[] = {&ws.counts, &ws.offsets, &ws.tile_sums, &ws.sorted, &ws.digits, &ws.partials, &ws.chunk_out, &ws.window_out, &ws.misc};
+  DevBuf* bufs[] = {&ws.counts, &ws.offsets, &ws.tile_sums, &ws.sorted, &ws.digits, &ws.partials, &ws.chunk_out, &ws.window_out, &ws.misc,
+                    &ws.lvl_off, &ws.pair_tab, &ws.pair_a, &ws.pair_b, &ws.pair_pre, &ws.lvl_pts};
   for (DevBuf* b : bufs)
     if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
 }

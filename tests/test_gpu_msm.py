@@ -274,3 +274,65 @@ def test_error_paths(ctx):
     with pytest.raises(ozl.OzlError):
         h2 = ozl.Bases(ctx, 12345, ozl.BN254_G1, 4)
         h2.msm(np.zeros((1, 4), dtype=np.uint64))
+
+
+@pytest.mark.parametrize("name", CURVES)
+@pytest.mark.parametrize("levels", [1, 3, 5])
+def test_msm_batch_affine_levels(ctx, name, levels):
+    """Experimental batched-affine pair levels (msm_batch.cuh) give the same group element:
+    directed scalars, and buckets built to hit every exceptional pair -- P + P (tangent),
+    P + (-P) (cancellation), a cancelled pair meeting a live one on the next level, and
+    buckets that cancel completely."""
+    n = 1 << 11 if name.endswith("g1") else 1 << 9
+    bases = cbind.bases_seq(name, 11, n)
+    c = curves.CURVES[name]
+    neg = lambda row: np.array(c.affine_to_mont_limbs(c.neg(c.affine_from_mont_limbs(list(row)))), dtype=np.uint64)
+    scalars = directed_scalars(name, n, seed=levels)
+    # same scalar -> same bucket in every window; sorted order inside a bucket is not fixed, so use
+    # groups where ANY pairing hits an exceptional case
+    k = 40
+    for j in range(1, 4):
+        bases[k + j] = bases[k]              # four copies of P: tangent pairs at two levels
+        scalars[k + j] = scalars[k]
+    k = 60
+    bases[k + 1] = neg(bases[k])             # P, -P, P, -P: cancels whatever the pairing
+    bases[k + 2] = bases[k]
+    bases[k + 3] = neg(bases[k])
+    for j in range(1, 4):
+        scalars[k + j] = scalars[k]
+    k = 80
+    bases[k + 1] = neg(bases[k])             # P, -P, Q: identity meets a live point
+    scalars[k + 1] = scalars[k]
+    scalars[k + 2] = scalars[k]
+    exp, exp_inf = oracle_affine(name, bases, scalars)
+    h = ctx.upload_bases(ozl.CURVE_IDS[name], bases)
+    try:
+        ctx.set_window_bits(6)               # few buckets -> long lists, several live levels
+        ctx.set_batch_affine(levels)
+        got, got_inf = gpu_affine(ctx, name, h.msm(scalars))
+    finally:
+        ctx.set_batch_affine(-1)
+        ctx.set_window_bits(0)
+        h.free()
+    assert got_inf == exp_inf
+    assert (got == exp).all()
+
+
+def test_msm_batch_affine_all_equal_and_tiny(ctx):
+    """One bucket holding every point (all scalars equal) and sizes around the pairing edge cases."""
+    name = "bn254_g1"
+    r = curves.CURVES[name].fr.p
+    try:
+        ctx.set_batch_affine(4)
+        for n in (1, 2, 3, 5, 33, 1000):
+            bases = cbind.bases_seq(name, 5, n)
+            scalars = np.repeat(ints_to_array([0x1234567 % r]), n, axis=0)
+            exp, exp_inf = oracle_affine(name, bases, scalars)
+            h = ctx.upload_bases(ozl.BN254_G1, bases)
+            try:
+                got, got_inf = gpu_affine(ctx, name, h.msm(scalars))
+            finally:
+                h.free()
+            assert got_inf == exp_inf and (got == exp).all(), n
+    finally:
+        ctx.set_batch_affine(-1)
