@@ -427,8 +427,10 @@ def run_groth16(args):
     ctx = ozl.Context(0)
     rnd = random.Random(2026)
     td = Trapdoor(*[rnd.randrange(2, p) for _ in range(5)])
+    if args.window_bits:
+        ctx.set_window_bits(args.window_bits)
     t0 = time.perf_counter()
-    pk, vk = Groth16.compile(ctx, "bn254", r1, td)
+    pk, vk = Groth16.compile(ctx, "bn254", r1, td, precompute=args.g16_precompute)
     t_setup = time.perf_counter() - t0
     zt = torch.from_numpy(z_m.view(np.int64)).pin_memory()
     z_pinned = zt.numpy().view(np.uint64)
@@ -471,7 +473,7 @@ def run_groth16(args):
         workers = [(ctx, pk)]
         for _ in range(args.concurrency - 1):
             c2 = ozl.Context(0)
-            workers.append((c2, Groth16.compile(c2, "bn254", r1, td)[0]))
+            workers.append((c2, Groth16.compile(c2, "bn254", r1, td, precompute=args.g16_precompute)[0]))
         def run(w, k):
             for _ in range(k):
                 Groth16.prove_with_randomness(w[1], z_pinned, r, s)
@@ -577,6 +579,7 @@ def main():
     ap.add_argument("--cpu-log-n", type=int, default=20)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--precompute", type=int, default=0, help="shifted base copies kept in HBM (1 = none, 0 = best measured for the size)")
+    ap.add_argument("--g16-precompute", type=int, default=16, help="groth16: shifted copies of each proving-key query")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -294,11 +294,36 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
   CUDA_TRY(ctx, cudaEventRecord(pk.ev_z, st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(pk.s1, pk.ev_z, 0));
   CUDA_TRY(ctx, cudaStreamWaitEvent(pk.s2, pk.ev_z, 0));
+  // Proof assembly terms are issued where their inputs become available, so only the final sums and
+  // the affine conversion remain after the last MSM:
+  //   s2: [s]alpha1, [r]beta1, [rs]delta1, [r]delta1, [s]delta2 (fixed tables; need only r, s), then the b2 MSM
+  //   s1: a MSM, b1 MSM, then [s]a_acc and [r]b1_acc, then the l MSM
+  static const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t* const S = pk.rs;                // 16+ scalars x 8 words: [0]=r [1]=s [2]=1 [3]=rs
+  uint32_t* const fs = S + 32;              // 4 scalars for the fixed G1 tables (alpha1, beta1, delta1, delta1)
+  uint32_t* const vs = S + 64;              // 2 scalars for the variable points
+  uint32_t* const fixed_out = acc + 12 * J1;     // s*alpha1, r*beta1, rs*delta1, r*delta1
+  uint32_t* const var_out = acc + 16 * J1;       // s*a_acc, r*b1_acc
+  uint32_t* const g2_fixed_out = acc_g2 + J2;    // s*delta2
+  auto cp_on = [&](cudaStream_t q, uint32_t* dst, const uint32_t* src, size_t words) {
+    return cudaMemcpyAsync(dst, src, words * 4, cudaMemcpyDeviceToDevice, q);
+  };
   {
     auto& reg = ctx->bases;
+    CUDA_TRY(ctx, cudaMemcpyAsync(S + 16, one, 32, cudaMemcpyHostToDevice, pk.s2));
+    f->mul_canonical(pk.s2, S + 0, S + 8, S + 24);
+    CUDA_TRY(ctx, cp_on(pk.s2, fs + 0, S + 8, 8));
+    CUDA_TRY(ctx, cp_on(pk.s2, fs + 8, S + 0, 8));
+    CUDA_TRY(ctx, cp_on(pk.s2, fs + 16, S + 24, 8));
+    CUDA_TRY(ctx, cp_on(pk.s2, fs + 24, S + 0, 8));
+    o1->scalar_mul_table(pk.s2, pk.tables_g1, fs, 4, fixed_out);
+    o2->scalar_mul_table(pk.s2, pk.tables_g2, S + 8, 1, g2_fixed_out);
     if ((rc = ozl_rt_msm(ctx, pk.ws2, pk.s2, reg[pk.h_b2], pk.zc, m, acc_g2))) return rc;
     if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, reg[pk.h_a], pk.zc, m, acc + 2 * J1))) return rc;
     if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, reg[pk.h_b1], pk.zc, m, acc + 3 * J1))) return rc;
+    CUDA_TRY(ctx, cp_on(pk.s1, vs + 0, pk.rs + 8, 8));
+    CUDA_TRY(ctx, cp_on(pk.s1, vs + 8, pk.rs + 0, 8));
+    o1->scalar_mul_var(pk.s1, acc + 2 * J1, vs, 2, var_out);   // acc[2] = a_acc, acc[3] = b1_acc (adjacent)
     if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, reg[pk.h_l], pk.zc + (size_t)ni * 8, m - ni, acc + 1 * J1))) return rc;
     CUDA_TRY(ctx, cudaEventRecord(pk.ev_s1, pk.s1));
     CUDA_TRY(ctx, cudaEventRecord(pk.ev_s2, pk.s2));
@@ -330,29 +355,8 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     STAGE(ctx, "g16_assemble");
     // C = l + h + [s]alpha1 + [r]beta1 + [rs]delta1 + [s]a_acc + [r]b1_acc      (= l + h + sA + rB1 - rs delta1)
     // A = alpha1 + a_acc + [r]delta1 ;  B = beta2 + b2_acc + [s]delta2
-    // scalars (8 words each) in pk.rs: [0]=r [1]=s [2]=1 [3]=rs ; lists from word 32*... below
-    static const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t* S = pk.rs;                    // 16 scalars x 8 words
-    CUDA_TRY(ctx, cudaMemcpyAsync(S + 16, one, 32, cudaMemcpyHostToDevice, st));
-    f->mul_canonical(st, S + 0, S + 8, S + 24);
-    auto cp = [&](uint32_t* dst, const uint32_t* src, size_t words) { return cudaMemcpyAsync(dst, src, words * 4, cudaMemcpyDeviceToDevice, st); };
-    // fixed-point terms (tables: alpha1, beta1, delta1, delta1) with scalars (s, r, rs, r)
-    uint32_t* fs = S + 32;                  // 4 scalars
-    CUDA_TRY(ctx, cp(fs + 0, S + 8, 8));
-    CUDA_TRY(ctx, cp(fs + 8, S + 0, 8));
-    CUDA_TRY(ctx, cp(fs + 16, S + 24, 8));
-    CUDA_TRY(ctx, cp(fs + 24, S + 0, 8));
-    uint32_t* fixed_out = acc + 12 * J1;    // 4 results: s*alpha1, r*beta1, rs*delta1, r*delta1
-    o1->scalar_mul_table(st, pk.tables_g1, fs, 4, fixed_out);
-    // variable-point terms: [s]a_acc, [r]b1_acc
-    uint32_t* vs = S + 64;                  // 2 scalars
-    CUDA_TRY(ctx, cp(vs + 0, S + 8, 8));
-    CUDA_TRY(ctx, cp(vs + 8, S + 0, 8));
-    uint32_t* var_out = acc + 16 * J1;      // 2 results
-    o1->scalar_mul_var(st, acc + 2 * J1, vs, 2, var_out);   // acc[2] = a_acc, acc[3] = b1_acc (adjacent)
-    // G2: [s]delta2
-    uint32_t* g2_fixed_out = acc_g2 + J2;
-    o2->scalar_mul_table(st, pk.tables_g2, S + 8, 1, g2_fixed_out);
+    // (the scalar multiples were issued on the side streams above)
+    auto cp = [&](uint32_t* dst, const uint32_t* src, size_t words) { return cp_on(st, dst, src, words); };
     // unit-scalar sums
     uint32_t* ones = S + 80;                // 8 unit scalars
     for (int i = 0; i < 8; i++) CUDA_TRY(ctx, cp(ones + 8 * i, S + 16, 8));
