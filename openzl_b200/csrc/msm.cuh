@@ -365,13 +365,17 @@ __device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& a, int delta) {
 // warp sums a group of up to 1024 of them (32 per lane + shuffle tree) into the group's first slot.
 // After the passes the bucket's total sits in its first slot and k_bucket_reduce reads only that.
 // ---------------------------------------------------------------------------------------------
-static constexpr uint32_t HEAVY_T = 8;
+// The threshold is relative to the average: heavy_t = max(HEAVY_T_MIN, 4 x the mean number of partials
+// per bucket), passed in by the host.  (With a fixed threshold of 8 EVERY bucket of a 2^28-point MSM
+// with few bucket sets counted as heavy and the collapse passes cost 236 ms.)
+static constexpr uint32_t HEAVY_T_MIN = 8;
 static constexpr uint32_t HEAVY_GROUP = 1024;
 static constexpr uint32_t HEAVY_GY = 16;
 
 template <class F>
 __global__ void __launch_bounds__(32)
-k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t NB, uint32_t L, uint32_t stride) {
+k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t NB, uint32_t L, uint32_t stride,
+                 uint32_t heavy_t) {
   constexpr int XY = 4 * F::N;
   const uint32_t lane = threadIdx.x;
   for (uint32_t g0 = blockIdx.x * 32; g0 < NB; g0 += gridDim.x * 32) {
@@ -385,7 +389,7 @@ k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ o
       }
     }
     const uint32_t live = (nparts + stride - 1) / stride;
-    uint32_t heavy = __ballot_sync(0xffffffffu, nparts > HEAVY_T && live > 1);
+    uint32_t heavy = __ballot_sync(0xffffffffu, nparts > heavy_t && live > 1);
     while (heavy) {
       const int src = __ffs(heavy) - 1;
       heavy &= heavy - 1;
@@ -421,7 +425,7 @@ k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ o
 template <class F>
 __global__ void __launch_bounds__(128)
 k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t L, uint32_t total_chunks,
-                uint32_t K, uint32_t B, uint32_t chunk, uint32_t* __restrict__ chunk_out) {
+                uint32_t K, uint32_t B, uint32_t chunk, uint32_t heavy_t, uint32_t* __restrict__ chunk_out) {
   constexpr int XY = 4 * F::N;
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total_chunks) return;
@@ -435,7 +439,7 @@ k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restric
     if (o1 > o0) {
       const uint32_t t0 = o0 / L;
       uint32_t t1 = (o1 - 1) / L;
-      if (t1 - t0 + 1 > HEAVY_T) t1 = t0;   // collapsed into its first slot by k_collapse_heavy
+      if (t1 - t0 + 1 > heavy_t) t1 = t0;   // collapsed into its first slot by k_collapse_heavy
       for (uint32_t t = t0; t <= t1; t++) {
         XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + t) * XY);
         running.add(p);

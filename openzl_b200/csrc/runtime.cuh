@@ -415,19 +415,22 @@ int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, con
   STAGE_END(ctx);
 
   STAGE_ON(ctx, "bucket_reduce", st);
+  // "heavy" = far more slice partials than the average bucket has (skew), not merely many
+  const uint32_t acc_entries = (uint32_t)std::min<uint64_t>(T ? ((((uint64_t)n * p.W) >> T) + p.NB) : (uint64_t)n * p.W, 0xffffffffull);
+  const uint32_t heavy_t = std::max<uint32_t>(HEAVY_T_MIN, 4u * (acc_entries / acc_L / p.NB + 2u));
   if (n) {
     // heavy-bucket collapse: 3 passes cover 2^30 partials per bucket; no-ops when nothing is heavy
     const dim3 hgrid((unsigned)std::min<uint32_t>((p.NB + 31) / 32, (uint32_t)ctx->sm_count * 16), HEAVY_GY);
     uint32_t stride = 1;
     for (int pass = 0; pass < 3; pass++) {
       if ((uint64_t)n * p.W / acc_L + 1 < stride) break;
-      k_collapse_heavy<F><<<hgrid, 32, 0, st>>>(partials, acc_offsets, p.NB, acc_L, stride);
+      k_collapse_heavy<F><<<hgrid, 32, 0, st>>>(partials, acc_offsets, p.NB, acc_L, stride, heavy_t);
       LAUNCH_CHECK(ctx);
       stride *= HEAVY_GROUP;
     }
   }
   const uint32_t total_chunks = (uint32_t)p.Wc * p.K;
-  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, acc_offsets, acc_L, total_chunks, p.K, p.B, p.chunk, chunk_out);
+  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, acc_offsets, acc_L, total_chunks, p.K, p.B, p.chunk, heavy_t, chunk_out);
   LAUNCH_CHECK(ctx);
   {
     const uint32_t Y = p.K >= 4096 ? 64 : 1;          // fan-out of the first summation launch
