@@ -214,16 +214,15 @@ def run_ours(args):
 
     ctx = ozl.Context(local_rank)
     ctx.use_torch_stream()
-    # --precompute 0 = measured best on B200: from 2^25 points a full set of shifted copies (one
-    # bucket set, c = 22: 12 windows, 72 GiB of bases at 2^26) beats 4 copies at c = 20 by 5 %
-    # (profiles/msm_sweep_c_r01.jsonl); below that 4 copies with the planner's window.
-    pre_window = 0
+    # --precompute 0 = measured best on B200 (profiles/msm_sweep_full_precompute_r01.jsonl): a FULL set
+    # of shifted copies -- one per window, so a single bucket set and no Horner tail -- whenever it
+    # fits in ~90 GB (2^26 points: c = 22, 12 copies, 72 GiB); otherwise up to 4 copies.  The
+    # planner picks the window width for the factor (c = 16 / 20 / 22 at 2^20 / 2^22-2^24 / 2^26).
     if args.precompute == 0:
-        max_copies = int(80e9 // (n * 96))           # keep the copies under ~80 GB of the 180 GB
-        if n >= (1 << 25) and max_copies >= 12 and not args.window_bits:
-            args.precompute, pre_window = 12, 22
+        if n * 96 * 13 <= 90e9:
+            args.precompute = 32                     # >= the number of windows: one copy per window
         else:
-            args.precompute = max(1, min(4, max_copies))
+            args.precompute = max(1, min(4, int(80e9 // (n * 96))))
     if args.window_bits:
         ctx.set_window_bits(args.window_bits)
     start = 1 + rank * n
@@ -262,8 +261,6 @@ def run_ours(args):
         value_plain = world * n / (p0.elapsed_time(p1) / 2 * 1e-3)
         c_plain = ctx.window_bits(curve, n)
         tpre = time.perf_counter()
-        if pre_window:
-            ctx.set_window_bits(pre_window)      # the copies are built for this window width
         bases.precompute(args.precompute)
         ctx.synchronize()
         tpre = time.perf_counter() - tpre
@@ -379,7 +376,7 @@ def run_ours(args):
         "dtype": "u32 limbs (Montgomery, 381-bit)", "data": "synthetic",
         "config": {"workload": f"BLS12-381 G1 Pippenger MSM, {_p2(n)} points per GPU ({_p2(world * n)} total), window c={c} ({W} windows in {Wc} bucket sets, signed digits)",
                    "bases": "P_i=[start+i]G generated on device, resident (constant across steps like a proving key)",
-                   "precompute_factor": args.precompute, "precompute_s": (tpre if args.precompute > 1 else 0.0),
+                   "precompute_factor": info["factor"], "precompute_s": (tpre if args.precompute > 1 else 0.0),
                    "value_without_precompute": value_plain,
                    "scalars": "uniform in [0,r), mask-and-reject", "l2": "inputs (8 GiB per step) are far larger than L2; no flush needed",
                    "parallelism": f"point-range shards x{world}, one NCCL all-gather of 144 B partials" if world > 1 else "single GPU"},
@@ -580,7 +577,7 @@ def main():
     ap.add_argument("--cpu-log-n", type=int, default=20)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--precompute", type=int, default=0, help="shifted base copies kept in HBM (1 = none, 0 = best measured for the size)")
-    ap.add_argument("--g16-precompute", type=int, default=16, help="groth16: shifted copies of each proving-key query")
+    ap.add_argument("--g16-precompute", type=int, default=32, help="groth16: shifted copies of each proving-key query")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

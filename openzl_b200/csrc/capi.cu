@@ -217,7 +217,7 @@ int ozl_msm_bases_free(ozl_ctx* ctx, uint32_t handle) {
 }
 
 int ozl_msm_bases_precompute(ozl_ctx* ctx, uint32_t handle, int factor) {
-  if (!ctx || factor < 1 || factor > 16) return OZL_ERR_ARG;
+  if (!ctx || factor < 1 || factor > 32) return OZL_ERR_ARG;
   Bases* b;
   int r = find_bases(ctx, handle, &b);
   if (r) return r;

@@ -182,7 +182,7 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0, in
     // n points of that window fall into a handful of buckets: hot atomics in the sort and heavy
     // buckets in the reduction (measured: c = 19 is 20 % slower than c = 20 at 2^24).  Skip such widths.
     const int top_bits = lambda + 1 - c * (W - 1);
-    if (c > 8 && top_bits < c - 6) continue;
+    if (c > 8 && top_bits < c - 8) continue;   // c - 8 admits c = 22 (14 live bits), measured best at 2^26 with one bucket set
     const double B = std::ldexp(1.0, c - 1);
     const double cost = (double)n * W * 10.0 + 2.0 * Wc * B * 95.0 + ((double)n * W / 128.0) * 45.0;
     if (cost < best) {
