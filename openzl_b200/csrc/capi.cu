@@ -223,11 +223,14 @@ int ozl_msm_bases_precompute(ozl_ctx* ctx, uint32_t handle, int factor) {
   if (r) return r;
   if (b->factor != 1) return OZL_ERR_ARG;  // already precomputed
   if (factor == 1 || b->n == 0) return OZL_OK;
-  if ((uint64_t)b->n * factor >= 0x7fffffffull) return OZL_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const MsmPlan p = make_plan(b->curve, b->n, ctx->forced_c, 0, factor);
   const int Wc = (p.W + factor - 1) / factor;
-  const int copies = (p.W + Wc - 1) / Wc;
+  const int copies = (p.W + Wc - 1) / Wc;        // a factor above the number of windows means one copy per window
+  if ((uint64_t)b->n * copies >= 0x7fffffffull) {
+    ctx->last_error = "bases_precompute: n * copies exceeds the 31-bit point index of the sorted entries";
+    return OZL_ERR_ARG;
+  }
   const size_t stride = (size_t)b->n * 2 * coord_u32(b->curve);
   uint32_t* nd = nullptr;
   CUDA_TRY(ctx, cudaMalloc((void**)&nd, stride * copies * 4));

@@ -336,3 +336,21 @@ def test_msm_batch_affine_all_equal_and_tiny(ctx):
             assert got_inf == exp_inf and (got == exp).all(), n
     finally:
         ctx.set_batch_affine(-1)
+
+
+@pytest.mark.parametrize("name", ["bls12_381_g1", "bn254_g2"])
+def test_msm_precompute_one_copy_per_window(ctx, name):
+    """A factor above the number of windows (what bench.py and the Groth16 bench pass: 32) means one
+    copy per window: a single bucket set, no Horner tail, same group element."""
+    n = 2000 if name.endswith("g1") else 500
+    bases = cbind.bases_seq(name, 9, n)
+    scalars = directed_scalars(name, n, seed=77)
+    exp, _ = oracle_affine(name, bases, scalars)
+    h = ctx.upload_bases(ozl.CURVE_IDS[name], bases).precompute(32)
+    try:
+        info = h.info(n)
+        assert info["bucket_sets"] == 1 and info["factor"] == info["windows"]
+        got, _ = gpu_affine(ctx, name, h.msm(scalars))
+        assert (got == exp).all()
+    finally:
+        h.free()
