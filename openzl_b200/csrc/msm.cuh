@@ -416,6 +416,28 @@ k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ o
   }
 }
 
+// Sum of each ordinary bucket's slice partials, one thread per bucket, into the bucket's first slot
+// (heavy buckets were already folded there by k_collapse_heavy).  Taking these additions out of
+// k_bucket_reduce shortens its dependent chain -- a lone thread pays ~15 us per 381-bit addition, so
+// the reduce stage of a small MSM is bound by chain length, not by work.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_bucket_fold(uint32_t* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t NB, uint32_t L, uint32_t heavy_t) {
+  constexpr int XY = 4 * F::N;
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= NB) return;
+  const uint32_t o0 = offsets[g], o1 = offsets[g + 1];
+  if (o1 <= o0) return;
+  const uint32_t t0 = o0 / L, t1 = (o1 - 1) / L;
+  if (t1 == t0 || t1 - t0 + 1 > heavy_t) return;
+  XYZZ<F> acc = XYZZ<F>::load(partials + (size_t)(g + t0) * XY);
+  for (uint32_t t = t0 + 1; t <= t1; t++) {
+    XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + t) * XY);
+    acc.add(p);
+  }
+  acc.store(partials + (size_t)(g + t0) * XY);
+}
+
 // ---------------------------------------------------------------------------------------------
 // bucket reduction: for a chunk of buckets [lo, lo + chunk) of window w computes
 //   sum_b (b + 1) * B_b   =   sum_b (b - lo + 1) B_b  +  lo * sum_b B_b
@@ -425,7 +447,7 @@ k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ o
 template <class F>
 __global__ void __launch_bounds__(128)
 k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t L, uint32_t total_chunks,
-                uint32_t K, uint32_t B, uint32_t chunk, uint32_t heavy_t, uint32_t* __restrict__ chunk_out) {
+                uint32_t K, uint32_t B, uint32_t chunk, uint32_t* __restrict__ chunk_out) {
   constexpr int XY = 4 * F::N;
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total_chunks) return;
@@ -437,13 +459,9 @@ k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restric
     const uint32_t g = w * B + lo + j;
     const uint32_t o0 = offsets[g], o1 = offsets[g + 1];
     if (o1 > o0) {
-      const uint32_t t0 = o0 / L;
-      uint32_t t1 = (o1 - 1) / L;
-      if (t1 - t0 + 1 > heavy_t) t1 = t0;   // collapsed into its first slot by k_collapse_heavy
-      for (uint32_t t = t0; t <= t1; t++) {
-        XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + t) * XY);
-        running.add(p);
-      }
+      // the bucket's total sits in its first slot (k_bucket_fold / k_collapse_heavy)
+      XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + o0 / L) * XY);
+      running.add(p);
     }
     acc.add(running);
   }

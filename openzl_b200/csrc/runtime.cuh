@@ -209,6 +209,10 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0, in
   uint32_t chunk = p.B / 4096;
   if (chunk < 4) chunk = 4;
   if (chunk > 16) chunk = 16;
+  {
+    static const int kForceChunk = []() { const char* e = getenv("OZL_MSM_CHUNK"); return e ? atoi(e) : 0; }();
+    if (kForceChunk >= 1) chunk = (uint32_t)kForceChunk;
+  }
   if (chunk > p.B) chunk = p.B;
   p.chunk = chunk;
   p.K = p.B / chunk;
@@ -429,8 +433,12 @@ int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, con
       stride *= HEAVY_GROUP;
     }
   }
+  if (n) {
+    k_bucket_fold<F><<<(p.NB + 127) / 128, 128, 0, st>>>(partials, acc_offsets, p.NB, acc_L, heavy_t);
+    LAUNCH_CHECK(ctx);
+  }
   const uint32_t total_chunks = (uint32_t)p.Wc * p.K;
-  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, acc_offsets, acc_L, total_chunks, p.K, p.B, p.chunk, heavy_t, chunk_out);
+  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, acc_offsets, acc_L, total_chunks, p.K, p.B, p.chunk, chunk_out);
   LAUNCH_CHECK(ctx);
   {
     const uint32_t Y = p.K >= 4096 ? 64 : 1;          // fan-out of the first summation launch
