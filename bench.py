@@ -25,6 +25,7 @@ exchanged with one NCCL all-gather and summed (EC addition is not an NCCL reduct
 from __future__ import annotations
 
 import argparse
+import math
 import json
 import os
 import subprocess
@@ -38,6 +39,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 R381 = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+# DRAM traffic of the dominant kernel from the committed ncu --set full capture of this exact
+# configuration, keyed by (log2 n, window bits, base copies); other configurations report null.
+NCU_TRAFFIC = {(26, 22, 12): 157.988539e9 + 1.746420e9}
 METRIC = "bls12_381_g1_msm_points_per_sec"
 UNIT = "points/s"
 
@@ -387,7 +391,9 @@ def run_ours(args):
                               "api": "ozl_msm_submit x K + ozl_ctx_synchronize (H2D of step i+1 overlaps step i)"}},
         "gpu_launches": int(launches_timed),
         "roofline": {"kernel": "k_accumulate", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get((int(math.log2(n)), c, info["factor"])),
+                     "traffic_source": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01b_ncu_k_accumulate_2p26.csv (one gather of 96 B per point per window, at 64-byte DRAM granularity)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": acc,
                      "share_of_step": acc / ms_per_step},
         "fma_pipe": {"note": "binding roofline: 381-bit Montgomery multiplications on the integer fma pipe",
