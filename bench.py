@@ -236,20 +236,25 @@ def run_ours(args):
     h_scalars = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
     h_scalars.copy_(d_scalars)
     d_out = torch.zeros(18, dtype=torch.int64, device=dev)
-    gathered = torch.zeros(world * 18, dtype=torch.int64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB); inputs are >> L2 anyway
     launches0 = ctx.launch_count
 
+    # N > 1: the library's own NCCL communicator (ozl_comm_*): shard MSM, one ncclAllGather of the
+    # 144-byte partials and the device-side sum, all on the context's stream; torch.distributed is
+    # only the rendezvous, the barrier and the max-over-ranks of the timings.
+    comm = None
+    if world > 1:
+        from openzl_b200.multi_gpu import Comm
+        comm = Comm.from_torch(ctx)
+
     def step():
-        bases.msm_device(d_scalars.data_ptr(), n, d_out.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_out)
+        if comm is not None:
+            comm.msm_sharded_device(bases, d_scalars.data_ptr(), n, d_out.data_ptr())
+        else:
+            bases.msm_device(d_scalars.data_ptr(), n, d_out.data_ptr())
 
     def combine():
-        if world > 1:
-            pts = gathered.cpu().numpy().view(np.uint64).reshape(world, 18)
-            return ctx.jacobian_sum(curve, pts)
-        return d_out.cpu().numpy().view(np.uint64)
+        return d_out.cpu().numpy().view(np.uint64)      # the combined point on every rank when N > 1
 
     if args.precompute > 1:
         # one untimed reference point without precomputed copies (same kernels, W bucket sets)
@@ -308,16 +313,20 @@ def run_ours(args):
     out_host = np.zeros(18, dtype=np.uint64)
     flush.fill_(1)
     torch.cuda.synchronize()
-    bases.msm_host_ptr(h_scalars.data_ptr(), n, out_host)   # warm the H2D staging buffer
+    def e2e_call():
+        if comm is not None:      # ozl_msm_sharded: host scalars of the shard in, combined point out
+            ctx._check(ctx._lib.ozl_msm_sharded(ctx._h, comm._h, bases.handle, h_scalars.data_ptr(), n, out_host.ctypes.data),
+                       "ozl_msm_sharded")
+        else:
+            bases.msm_host_ptr(h_scalars.data_ptr(), n, out_host)
+
+    e2e_call()                                              # warm the H2D staging buffer
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        bases.msm_host_ptr(h_scalars.data_ptr(), n, out_host)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(out_host.view(np.int64)).to(dev))
-            combine()
+        e2e_call()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.steps
     if world > 1:
@@ -342,7 +351,11 @@ def run_ours(args):
         pipe_s = float(t.item())
     # Jacobian representatives depend on the (atomic) order of points inside a bucket: compare affine forms
     pipe_affine = [ctx.jacobian_to_affine(curve, o)[0] for o in outs.numpy().view(np.uint64)]
-    ref_affine = ctx.jacobian_to_affine(curve, out_host)[0]
+    ref_partial = out_host
+    if world > 1:                                           # submissions return this rank's partial
+        ref_partial = np.zeros(18, dtype=np.uint64)
+        bases.msm_host_ptr(h_scalars.data_ptr(), n, ref_partial)
+    ref_affine = ctx.jacobian_to_affine(curve, ref_partial)[0]
     pipe_ok = bool(all((a == ref_affine).all() for a in pipe_affine))
 
     # --- verification outside the timed region: sum s_i [start+i]G == [sum s_i (start+i)]G ----
@@ -383,10 +396,10 @@ def run_ours(args):
                    "precompute_factor": info["factor"], "precompute_s": (tpre if args.precompute > 1 else 0.0),
                    "value_without_precompute": value_plain,
                    "scalars": "uniform in [0,r), mask-and-reject", "l2": "inputs (8 GiB per step) are far larger than L2; no flush needed",
-                   "parallelism": f"point-range shards x{world}, one NCCL all-gather of 144 B partials" if world > 1 else "single GPU"},
+                   "parallelism": f"point-range shards x{world}, one ncclAllGather of 144 B partials + device-side sum on the MSM's stream (ozl_msm_sharded)" if world > 1 else "single GPU"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 144,
-                "ms_per_step": e2e_s * 1e3, "api": "ozl_msm (C ABI, pinned host scalars, bases resident)",
+                "ms_per_step": e2e_s * 1e3, "api": ("ozl_msm_sharded" if world > 1 else "ozl_msm") + " (C ABI, pinned host scalars, bases resident)",
                 "pipelined": {"value": world * n / pipe_s, "ms_per_step": pipe_s * 1e3, "results_identical": pipe_ok,
                               "api": "ozl_msm_submit x K + ozl_ctx_synchronize (H2D of step i+1 overlaps step i)"}},
         "gpu_launches": int(launches_timed),

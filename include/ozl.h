@@ -48,7 +48,8 @@ typedef enum {
   OZL_ERR_NO_DEVICE = 3,  /* no usable CUDA device                                             */
   OZL_ERR_OOM = 4,        /* device or host allocation failed                                  */
   OZL_ERR_HANDLE = 5,     /* unknown or freed bases handle                                     */
-  OZL_ERR_DOMAIN = 6      /* log_n exceeds the field's two-adicity (ark: `new` returns None)   */
+  OZL_ERR_DOMAIN = 6,     /* log_n exceeds the field's two-adicity (ark: `new` returns None)   */
+  OZL_ERR_NCCL = 7        /* libnccl.so.2 not loadable, or an NCCL call failed                 */
 } ozl_status;
 
 /* Groups behind `Pairing::{G1, G2}` (/root/reference/plugins/arkworks/src/pairing.rs:14-23). */
@@ -137,6 +138,28 @@ int ozl_jacobian_sum(ozl_ctx* ctx, int curve, const uint64_t* points, size_t k,
 /* GroupProjective::into_affine: writes x || y (zeros for the identity) and *is_identity. */
 int ozl_jacobian_to_affine(ozl_ctx* ctx, int curve, const uint64_t* jacobian, uint64_t* out_affine,
                            int* is_identity);
+
+/* ---- multi-GPU MSM: one rank per GPU, point-range shards, one all-gather of partials -------- */
+/* Sum_i s_i P_i = Sum_g Sum_{i in shard g} s_i P_i.  Every rank uploads ITS point range as a bases
+ * handle, runs the full single-GPU pipeline on its scalars, and the Jacobian partials are exchanged
+ * with one ncclAllGather on the context's stream and summed on the device (elliptic-curve addition
+ * is not an NCCL reduction op, so it is not an all-reduce).  The communicator is created from a
+ * 128-byte NCCL unique id that rank 0 makes and the caller distributes by its own means (MPI,
+ * torch.distributed, a file ...).  NCCL is bound at run time (dlopen of libnccl.so.2). */
+typedef struct ozl_comm ozl_comm;
+#define OZL_COMM_ID_BYTES 128
+int ozl_comm_unique_id(uint8_t* id_out /* OZL_COMM_ID_BYTES */);
+int ozl_comm_create(ozl_ctx* ctx, const uint8_t* id, int rank, int world, ozl_comm** out);
+int ozl_comm_destroy(ozl_comm* comm);
+/* Host scalars of this rank's shard in, the COMBINED result (identical on every rank) out. */
+int ozl_msm_sharded(ozl_ctx* ctx, ozl_comm* comm, uint32_t handle, const uint64_t* scalars, size_t n,
+                    uint64_t* out_jacobian);
+/* Same with device scalars / device output, enqueued on the context's stream. */
+int ozl_msm_sharded_device_async(ozl_ctx* ctx, ozl_comm* comm, uint32_t handle, const uint64_t* d_scalars,
+                                 size_t n, uint64_t* d_out_jacobian);
+/* The combine step alone: all-gather one device-resident Jacobian partial per rank and sum. */
+int ozl_comm_allgather_sum_async(ozl_ctx* ctx, ozl_comm* comm, int curve, const uint64_t* d_partial,
+                                 uint64_t* d_out_jacobian);
 
 /* ---- NTT: replaces Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place ------- */
 /* data = 2^log_n elements x 4 u64 limbs, Montgomery, natural order in and out, in place.

@@ -30,6 +30,8 @@ EXPORTS = [
     "ozl_jacobian_to_affine", "ozl_ntt", "ozl_ntt_device_async", "ozl_ctx_enable_timing",
     "ozl_ctx_get_stage_times", "ozl_ctx_launch_count", "ozl_bench_field_mul", "ozl_fr_spmv", "ozl_fixed_base_mul",
     "ozl_groth16_pk_create", "ozl_groth16_pk_destroy", "ozl_groth16_prove", "ozl_groth16_domain_size",
+    "ozl_comm_unique_id", "ozl_comm_create", "ozl_comm_destroy", "ozl_msm_sharded", "ozl_msm_sharded_device_async",
+    "ozl_comm_allgather_sum_async",
 ]
 
 
@@ -95,6 +97,12 @@ def load() -> ctypes.CDLL:
     lib.ozl_msm_submit.argtypes = [vp, ctypes.c_uint32, vp, sz, vp]
     lib.ozl_msm_device_async.argtypes = [vp, ctypes.c_uint32, vp, sz, vp]
     lib.ozl_msm_set_window_bits.argtypes = [vp, ctypes.c_int]
+    lib.ozl_comm_unique_id.argtypes = [vp]
+    lib.ozl_comm_create.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    lib.ozl_comm_destroy.argtypes = [vp]
+    lib.ozl_msm_sharded.argtypes = [vp, vp, ctypes.c_uint32, vp, sz, vp]
+    lib.ozl_msm_sharded_device_async.argtypes = [vp, vp, ctypes.c_uint32, vp, sz, vp]
+    lib.ozl_comm_allgather_sum_async.argtypes = [vp, vp, ctypes.c_int, vp, vp]
     lib.ozl_msm_set_batch_affine.argtypes = [vp, ctypes.c_int]
     lib.ozl_msm_get_window_bits.argtypes = [vp, ctypes.c_int, sz]
     ip = ctypes.POINTER(ctypes.c_int)

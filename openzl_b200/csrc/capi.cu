@@ -60,6 +60,7 @@ const char* ozl_strerror(int s) {
     case OZL_ERR_OOM: return "out of memory";
     case OZL_ERR_HANDLE: return "unknown bases handle";
     case OZL_ERR_DOMAIN: return "domain larger than the field's two-adicity";
+    case OZL_ERR_NCCL: return "NCCL unavailable or an NCCL call failed";
   }
   return "unknown status";
 }

@@ -53,3 +53,71 @@ def msm_sharded_gpu(ctx, bases, scalars_shard: np.ndarray, group=None) -> np.nda
     dev = torch.device("cuda", ctx.device)
     return msm_sharded(lambda: bases.msm(scalars_shard), lambda pts: ctx.jacobian_sum(bases.curve, pts), group=group,
                        device=dev)
+
+
+class Comm:
+    """``ozl_comm``: the library's own NCCL communicator for the sharded MSM (include/ozl.h).
+
+    ``Comm.from_torch(ctx, group)`` makes the 128-byte NCCL unique id on rank 0, broadcasts it through
+    ``torch.distributed`` (any backend -- this is only the rendezvous) and joins every rank.  After
+    that the shard MSM, the all-gather of partials and their sum run on the context's stream with
+    no host hop: ``comm.msm_sharded(bases, scalars_shard)``."""
+
+    ID_BYTES = 128
+
+    def __init__(self, ctx, handle, rank: int, world: int):
+        self.ctx, self._h, self.rank, self.world = ctx, handle, rank, world
+
+    @staticmethod
+    def unique_id(lib) -> bytes:
+        import ctypes
+        buf = (ctypes.c_uint8 * Comm.ID_BYTES)()
+        rc = lib.ozl_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p))
+        if rc:
+            from ._lib import OzlError
+            raise OzlError(rc, "ozl_comm_unique_id", lib.ozl_strerror(rc).decode())
+        return bytes(buf)
+
+    @staticmethod
+    def exchange_id(make_id: Callable[[], bytes], group=None) -> bytes:
+        """Rank 0 calls ``make_id``; every rank returns the same bytes (torch.distributed broadcast)."""
+        import torch.distributed as dist
+        box = [make_id() if dist.get_rank(group) == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return box[0]
+
+    @classmethod
+    def create(cls, ctx, uid: bytes, rank: int, world: int) -> "Comm":
+        import ctypes
+        if len(uid) != cls.ID_BYTES:
+            raise ValueError("NCCL unique id must be 128 bytes")
+        buf = (ctypes.c_uint8 * cls.ID_BYTES).from_buffer_copy(uid)
+        h = ctypes.c_void_p()
+        ctx._check(ctx._lib.ozl_comm_create(ctx._h, ctypes.cast(buf, ctypes.c_void_p), rank, world, ctypes.byref(h)),
+                   "ozl_comm_create")
+        return cls(ctx, h, rank, world)
+
+    @classmethod
+    def from_torch(cls, ctx, group=None) -> "Comm":
+        import torch.distributed as dist
+        uid = cls.exchange_id(lambda: cls.unique_id(ctx._lib), group)
+        return cls.create(ctx, uid, dist.get_rank(group), dist.get_world_size(group))
+
+    def msm_sharded(self, bases, scalars_shard: np.ndarray) -> np.ndarray:
+        """This rank's shard in (host scalars), the combined Jacobian result out (same on every rank)."""
+        scalars_shard = np.ascontiguousarray(scalars_shard, dtype=np.uint64)
+        n = scalars_shard.shape[0]
+        out = np.zeros(3 * bases.coord_limbs, dtype=np.uint64)
+        self.ctx._check(self.ctx._lib.ozl_msm_sharded(self.ctx._h, self._h, bases.handle, scalars_shard.ctypes.data if n else None,
+                                                      n, out.ctypes.data), "ozl_msm_sharded")
+        return out
+
+    def msm_sharded_device(self, bases, d_scalars: int, n: int, d_out: int) -> None:
+        """Device pointers, enqueued on the context's stream (no synchronisation)."""
+        self.ctx._check(self.ctx._lib.ozl_msm_sharded_device_async(self.ctx._h, self._h, bases.handle, d_scalars, n, d_out),
+                        "ozl_msm_sharded_device_async")
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.ozl_comm_destroy(self._h)
+            self._h = None

@@ -80,3 +80,50 @@ def test_sharded_msm_world2_gloo():
     exp = c.affine_from_mont_limbs(list(exp_limbs))
     assert all(aff == exp for _, aff in results)
     assert sorted(r for r, _ in results) == [0, 1]
+
+
+def _id_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from openzl_b200.multi_gpu import Comm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    calls = []
+
+    def make():
+        calls.append(rank)
+        return bytes(range(128))
+    uid = Comm.exchange_id(make)
+    q.put((rank, uid, len(calls)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_comm_id_exchange_world2_gloo():
+    """The rendezvous of the library's own NCCL communicator: only rank 0 makes the unique id,
+    every rank ends up with the same 128 bytes."""
+    world, port = 2, _free_port()
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    procs = [ctxmp.Process(target=_id_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert [g[1] for g in got] == [bytes(range(128))] * world
+    assert [g[2] for g in got] == [1, 0]
+
+
+def test_comm_entry_points_reject_bad_arguments():
+    """No GPU here: the communicator entry points must fail with a status, never crash."""
+    import ctypes
+    from openzl_b200 import _lib
+    lib = _lib.load()
+    assert lib.ozl_comm_unique_id(None) == 1                       # OZL_ERR_ARG
+    h = ctypes.c_void_p()
+    buf = (ctypes.c_uint8 * 128)()
+    assert lib.ozl_comm_create(None, ctypes.cast(buf, ctypes.c_void_p), 0, 1, ctypes.byref(h)) == 1
+    assert lib.ozl_msm_sharded(None, None, 0, None, 0, None) == 1
+    assert lib.ozl_comm_destroy(None) == 0
+    assert b"NCCL" in lib.ozl_strerror(7)
