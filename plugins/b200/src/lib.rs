@@ -28,7 +28,18 @@ extern "C" {
     fn ozl_msm_bases_free(ctx: *mut OzlCtx, handle: u32) -> c_int;
     fn ozl_msm(ctx: *mut OzlCtx, handle: u32, scalars: *const u64, n: usize, out_jacobian: *mut u64) -> c_int;
     fn ozl_ntt(ctx: *mut OzlCtx, field: c_int, data: *mut u64, log_n: u32, inverse: c_int, coset: c_int) -> c_int;
+    // multi-GPU: one process (rank) per GPU, each holding its point range of the query vector
+    fn ozl_comm_unique_id(id_out: *mut u8) -> c_int;
+    fn ozl_comm_create(ctx: *mut OzlCtx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut OzlComm) -> c_int;
+    fn ozl_comm_destroy(comm: *mut OzlComm) -> c_int;
+    fn ozl_msm_sharded(ctx: *mut OzlCtx, comm: *mut OzlComm, handle: u32, scalars: *const u64, n: usize, out_jacobian: *mut u64) -> c_int;
 }
+
+#[repr(C)]
+pub struct OzlComm {
+    _private: [u8; 0],
+}
+pub const OZL_COMM_ID_BYTES: usize = 128;
 
 pub const OZL_BLS12_381_G1: c_int = 0;
 pub const OZL_BLS12_381_G2: c_int = 1;
@@ -101,6 +112,51 @@ impl<'c> G1Bases381<'c> {
         }
         let fq = |o: usize| ark_bls12_381::Fq::new(BigInteger384([out[o], out[o + 1], out[o + 2], out[o + 3], out[o + 4], out[o + 5]]));
         Ok(ark_bls12_381::G1Projective::new(fq(0), fq(6), fq(12))) // Fp::new takes the Montgomery representation
+    }
+}
+
+/// The library's NCCL communicator over the ranks that share one MSM (one rank per GPU).
+/// Rank 0 calls `Comm::unique_id()` and ships the 128 bytes to the other ranks by the
+/// application's own means; every rank then calls `Comm::join`.
+pub struct Comm<'c> {
+    ctx: &'c Context,
+    raw: *mut OzlComm,
+}
+
+impl<'c> Comm<'c> {
+    pub fn unique_id() -> Result<[u8; OZL_COMM_ID_BYTES], Error> {
+        let mut id = [0u8; OZL_COMM_ID_BYTES];
+        match unsafe { ozl_comm_unique_id(id.as_mut_ptr()) } {
+            0 => Ok(id),
+            _ => Err(Error),
+        }
+    }
+    pub fn join(ctx: &'c Context, id: &[u8; OZL_COMM_ID_BYTES], rank: i32, world: i32) -> Result<Self, Error> {
+        let mut raw = core::ptr::null_mut();
+        match unsafe { ozl_comm_create(ctx.0, id.as_ptr(), rank, world, &mut raw) } {
+            0 => Ok(Self { ctx, raw }),
+            _ => Err(Error),
+        }
+    }
+}
+
+impl Drop for Comm<'_> {
+    fn drop(&mut self) {
+        unsafe { ozl_comm_destroy(self.raw) };
+    }
+}
+
+impl<'c> G1Bases381<'c> {
+    /// `multi_scalar_mul` over a query vector split by point range across the ranks of `comm`:
+    /// `self` holds THIS rank's range, `scalars` the matching slice; the full sum comes back on every rank.
+    pub fn multi_scalar_mul_sharded(&self, comm: &Comm<'c>, scalars: &[<ark_bls12_381::Fr as PrimeField>::BigInt]) -> Result<ark_bls12_381::G1Projective, Error> {
+        let n = core::cmp::min(self.n, scalars.len());
+        let mut out = [0u64; 18];
+        if unsafe { ozl_msm_sharded(self.ctx.0, comm.raw, self.handle, scalars.as_ptr() as *const u64, n, out.as_mut_ptr()) } != 0 {
+            return Err(Error);
+        }
+        let fq = |o: usize| ark_bls12_381::Fq::new(BigInteger384([out[o], out[o + 1], out[o + 2], out[o + 3], out[o + 4], out[o + 5]]));
+        Ok(ark_bls12_381::G1Projective::new(fq(0), fq(6), fq(12)))
     }
 }
 
