@@ -81,6 +81,15 @@ def test_prove_matches_oracle_and_verifies(ctx, links):
         for name, k, got in (("bn254_g1", A, proof.a), ("bn254_g2", B, proof.b), ("bn254_g1", C, proof.c)):
             exp, exp_inf = cbind.to_affine(name, cbind.gen_mul(name, k))
             assert not exp_inf and (got == exp).all(), name
+        # wire format (groth16.rs:98-107): 128 compressed bytes that decode back to the same three points
+        from openzl_b200 import serialize as ser
+        raw = proof.to_bytes("bn254")
+        assert len(raw) == 128
+        pa, pb, pc = ser.proof_from_bytes("bn254", raw)
+        assert ser.is_on_curve(ser.BN254_G1, pa) and ser.is_on_curve(ser.BN254_G2, pb) and ser.is_on_curve(ser.BN254_G1, pc)
+        assert (ser.point_to_limbs(ser.BN254_G1, pa) == proof.a).all()
+        assert (ser.point_to_limbs(ser.BN254_G2, pb) == proof.b).all()
+        assert (ser.point_to_limbs(ser.BN254_G1, pc) == proof.c).all()
         # r = s = 0 (the degenerate blinding ark special-cases) still matches
         proof0 = Groth16.prove_with_randomness(pk, z_m, 0, 0)
         A0, B0, C0 = og.prove_exponents("bn254_fr", r1, z, td, 0, 0, h=h)
