@@ -79,13 +79,17 @@ static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8
 
 // Counting-sort scatter of ONE window: the window's cursors (2^(c-1) words), offsets and the
 // 32-byte sectors being filled all stay L2-resident, so each sector of `sorted` reaches HBM once.
+// [key_lo, key_hi) restricts a launch to a range of buckets: with many buckets (2^21 at c = 22) the
+// open 32-byte sectors of ALL buckets no longer fit in L2 and get evicted half-filled; scattering one
+// bucket range at a time keeps them resident at the price of re-reading the 4-byte digits.
 static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, uint32_t n, uint32_t g_base,
                                         uint32_t idx_offset, const uint32_t* __restrict__ offsets,
                                         uint32_t* __restrict__ cursor,
-                                        uint32_t* __restrict__ sorted) {
+                                        uint32_t* __restrict__ sorted, uint32_t key_lo, uint32_t key_hi) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t d = digits_w[i];
-    const uint32_t key = d & 0x7fffffffu;
+    uint32_t key = d & 0x7fffffffu;
+    if (key <= key_lo || key > key_hi) key = 0;       // keys are bucket + 1
     // warp-aggregated cursor update: one atomic per distinct bucket per warp
     const uint32_t active = __activemask();
     const uint32_t peers = __match_any_sync(active, key);
