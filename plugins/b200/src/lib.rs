@@ -11,6 +11,8 @@
 //! `into_repr()` yields the canonical `BigInteger256` the MSM takes, so slices cross the boundary
 //! without conversion.  `GroupAffine` is not `repr(C)` (x, y, infinity + padding), hence the packing.
 
+pub mod groth16; // Groth16B200: ProofSystem (prove on the device, compile / verify with arkworks)
+
 use ark_ec::AffineCurve;
 use ark_ff::{BigInteger256, BigInteger384, PrimeField};
 use std::os::raw::c_int;
