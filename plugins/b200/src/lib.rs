@@ -177,3 +177,82 @@ pub fn ntt_in_place_bn254(ctx: &Context, v: &mut [ark_bn254::Fr], inverse: bool,
         _ => Err(Error),
     }
 }
+
+/// Curve-generic bases handle used by `groth16::Groth16B200` (BN254: 4 u64 limbs per Fq).
+pub struct Bases {
+    ctx: *mut OzlCtx,
+    handle: u32,
+    n: usize,
+}
+
+impl Bases {
+    fn upload(ctx: &Context, curve: c_int, packed: &[u64], inf: &[u8], n: usize, precompute: i32) -> Result<Self, Error> {
+        let mut handle = 0u32;
+        if unsafe { ozl_msm_bases_upload(ctx.0, curve, packed.as_ptr(), inf.as_ptr(), n, &mut handle) } != 0 {
+            return Err(Error);
+        }
+        if precompute > 1 && unsafe { ozl_msm_bases_precompute(ctx.0, handle, precompute) } != 0 {
+            return Err(Error);
+        }
+        Ok(Self { ctx: ctx.0, handle, n })
+    }
+
+    pub fn upload_g1_bn254(ctx: &Context, bases: &[ark_bn254::G1Affine], precompute: i32) -> Result<Self, Error> {
+        let mut packed = Vec::<u64>::with_capacity(bases.len() * 8);
+        let mut inf = vec![0u8; (bases.len() + 7) / 8];
+        for (i, p) in bases.iter().enumerate() {
+            if p.is_zero() {
+                inf[i / 8] |= 1 << (i % 8);
+                packed.extend_from_slice(&[0u64; 8]);
+            } else {
+                packed.extend_from_slice(&p.x.0 .0);
+                packed.extend_from_slice(&p.y.0 .0);
+            }
+        }
+        Self::upload(ctx, OZL_BN254_G1, &packed, &inf, bases.len(), precompute)
+    }
+
+    pub fn upload_g2_bn254(ctx: &Context, bases: &[ark_bn254::G2Affine], precompute: i32) -> Result<Self, Error> {
+        let mut packed = Vec::<u64>::with_capacity(bases.len() * 16);
+        let mut inf = vec![0u8; (bases.len() + 7) / 8];
+        for (i, p) in bases.iter().enumerate() {
+            if p.is_zero() {
+                inf[i / 8] |= 1 << (i % 8);
+                packed.extend_from_slice(&[0u64; 16]);
+            } else {
+                for c in [&p.x.c0, &p.x.c1, &p.y.c0, &p.y.c1] {
+                    packed.extend_from_slice(&c.0 .0);   // x.c0 || x.c1 || y.c0 || y.c1, Montgomery limbs
+                }
+            }
+        }
+        Self::upload(ctx, OZL_BN254_G2, &packed, &inf, bases.len(), precompute)
+    }
+
+    fn msm_raw<const LIMBS: usize>(&self, scalars: &[BigInteger256]) -> Result<[u64; LIMBS], Error> {
+        let n = core::cmp::min(self.n, scalars.len());
+        let mut out = [0u64; LIMBS];
+        match unsafe { ozl_msm(self.ctx, self.handle, scalars.as_ptr() as *const u64, n, out.as_mut_ptr()) } {
+            0 => Ok(out),
+            _ => Err(Error),
+        }
+    }
+
+    pub fn msm_g1_bn254(&self, scalars: &[BigInteger256]) -> Result<ark_bn254::G1Projective, Error> {
+        let o = self.msm_raw::<12>(scalars)?;
+        let fq = |k: usize| ark_bn254::Fq::new(BigInteger256([o[k], o[k + 1], o[k + 2], o[k + 3]]));
+        Ok(ark_bn254::G1Projective::new(fq(0), fq(4), fq(8)))
+    }
+
+    pub fn msm_g2_bn254(&self, scalars: &[BigInteger256]) -> Result<ark_bn254::G2Projective, Error> {
+        let o = self.msm_raw::<24>(scalars)?;
+        let fq = |k: usize| ark_bn254::Fq::new(BigInteger256([o[k], o[k + 1], o[k + 2], o[k + 3]]));
+        let fq2 = |k: usize| ark_bn254::Fq2::new(fq(k), fq(k + 4));
+        Ok(ark_bn254::G2Projective::new(fq2(0), fq2(8), fq2(16)))
+    }
+}
+
+impl Drop for Bases {
+    fn drop(&mut self) {
+        unsafe { ozl_msm_bases_free(self.ctx, self.handle) };
+    }
+}
