@@ -86,15 +86,15 @@ static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, u
                                         uint32_t idx_offset, const uint32_t* __restrict__ offsets,
                                         uint32_t* __restrict__ cursor,
                                         uint32_t* __restrict__ sorted, uint32_t key_lo, uint32_t key_hi) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t d = digits_w[i];
+  const uint32_t lane = threadIdx.x & 31u;
+  // one entry: warp-aggregated cursor update (one atomic per distinct bucket per warp), then the write
+  auto place = [&](uint32_t i, uint32_t d, bool valid) {
     uint32_t key = d & 0x7fffffffu;
-    if (key <= key_lo || key > key_hi) key = 0;       // keys are bucket + 1
-    // warp-aggregated cursor update: one atomic per distinct bucket per warp
+    if (!valid || key <= key_lo || key > key_hi) key = 0;       // keys are bucket + 1
     const uint32_t active = __activemask();
+    if (__ballot_sync(active, key != 0) == 0) return;           // nothing of this range in the warp's 32 entries
     const uint32_t peers = __match_any_sync(active, key);
     if (key) {
-      const uint32_t lane = threadIdx.x & 31u;
       const int leader = __ffs(peers) - 1;
       const uint32_t g = g_base + key - 1u;
       uint32_t base = 0;
@@ -104,6 +104,26 @@ static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, u
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
       sorted[offsets[g] + base - 1u - rank] = (i + idx_offset) | (d & 0x80000000u);
     }
+  };
+  // 16-byte loads: four digits per thread per trip (n * 4 bytes is 16-byte aligned per window when n % 4 == 0)
+  const uint32_t n4 = ((reinterpret_cast<uintptr_t>(digits_w) & 15u) == 0) ? (n >> 2) : 0;
+  const uint4* d4 = reinterpret_cast<const uint4*>(digits_w);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t trips = (n4 + stride - 1) / stride;           // uniform trip count keeps the warps converged
+  for (uint32_t t = 0, j = blockIdx.x * blockDim.x + threadIdx.x; t < trips; t++, j += stride) {
+    const bool valid = j < n4;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (valid) v = d4[j];
+    place(4 * j + 0, v.x, valid);
+    place(4 * j + 1, v.y, valid);
+    place(4 * j + 2, v.z, valid);
+    place(4 * j + 3, v.w, valid);
+  }
+  const uint32_t tail0 = n4 << 2;
+  const uint32_t tail_trips = (n - tail0 + stride - 1) / stride;
+  for (uint32_t t = 0, i = tail0 + blockIdx.x * blockDim.x + threadIdx.x; t < tail_trips; t++, i += stride) {
+    const bool valid = i < n;
+    place(i, valid ? digits_w[i] : 0u, valid);
   }
 }
 
