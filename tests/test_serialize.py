@@ -168,3 +168,32 @@ def test_proving_key_round_trip(pairing):
     assert ser.limbs_to_points(g2, arr, mask) == back.b_g2_query
     vkb = ser.vk_to_bytes(pairing, vk)
     assert ser.vk_from_bytes(pairing, vkb)[0] == vk
+
+
+def test_random_byte_strings_never_crash_the_decoder():
+    """``deserialize`` on arbitrary bytes either returns a point on the curve or raises
+    SerializationError (ark: Err(SerializationError)); nothing else."""
+    rnd = random.Random(2026)
+    for _, g in PAIRS:
+        ok = 0
+        for _ in range(60):
+            raw = bytes(rnd.getrandbits(8) for _ in range(g.compressed_size))
+            try:
+                pt, off = ser.point_from_bytes(g, raw)
+            except ser.SerializationError:
+                continue
+            ok += 1
+            assert off == g.compressed_size and ser.is_on_curve(g, pt)
+            if pt is not None:
+                assert ser.point_to_bytes(g, pt) == raw          # canonical: re-encoding reproduces the bytes
+        assert ok < 60
+
+
+def test_limb_layout_matches_the_abi_for_g2():
+    """x.c0 || x.c1 || y.c0 || y.c1, each a little-endian Montgomery residue (include/ozl.h)."""
+    g = ser.BN254_G2
+    C = curves.CURVES["bn254_g2"]
+    P = _to_ser(g, C.gen)
+    limbs = ser.point_to_limbs(g, P)
+    assert list(limbs) == C.affine_to_mont_limbs(C.gen)
+    assert ser.limbs_to_point(g, limbs) == P
