@@ -52,6 +52,45 @@ def test_ntt_2_16_vs_oracle(ctx):
     assert (got == exp).all()
 
 
+@pytest.mark.parametrize("fname,fid", FIELDS)
+@pytest.mark.parametrize("inverse,coset", MODES)
+def test_ntt_2_20_vs_oracle(ctx, fname, fid, inverse, coset):
+    """Groth16's domain size (BASELINE config 3 lower end): every mode, both fields, all 2^20 outputs
+    bit-for-bit against the C++ oracle (under a second on the CPU)."""
+    f = fields.FIELDS[fname]
+    x = random_scalars(1 << 20, f.p, seed=17 + 2 * inverse + coset)
+    exp = cbind.ntt(fname, x, inverse=inverse, coset=coset)
+    got = x.copy()
+    ctx.ntt(fid, got, inverse=inverse, coset=coset)
+    assert (got == exp).all()
+
+
+def test_ntt_2_24_linearity_and_round_trip(ctx):
+    """BASELINE config 3 upper end, through size-independent properties: for a sparse s (64 non-zero
+    entries) NTT(a + s) = NTT(a) + NTT(s) on 4096 sampled outputs, and coset_ifft(coset_fft(a)) = a
+    on all 2^24 elements."""
+    p = fields.BN254_FR.p
+    n = 1 << 24
+    a = random_scalars(n, p, seed=1)
+    to_int = lambda rows: [int.from_bytes(r.tobytes(), "little") for r in rows]
+    hot = np.unique(np.random.default_rng(4).integers(0, n, size=64))
+    s_vals = random_scalars(hot.size, p, seed=2)
+    sp = np.zeros_like(a)
+    sp[hot] = s_vals
+    c = a.copy()
+    for j, va, vs in zip(hot, to_int(a[hot]), to_int(s_vals)):
+        c[j] = np.frombuffer(((va + vs) % p).to_bytes(32, "little"), dtype=np.uint64)
+    fa, fs, fc = a.copy(), sp, c
+    for v in (fa, fs, fc):
+        ctx.ntt(ozl.BN254_FR, v)
+    idx = np.random.default_rng(3).integers(0, n, size=4096)
+    assert to_int(fc[idx]) == [(u + v) % p for u, v in zip(to_int(fa[idx]), to_int(fs[idx]))]
+    y = a.copy()
+    ctx.ntt(ozl.BN254_FR, y, coset=True)
+    ctx.ntt(ozl.BN254_FR, y, inverse=True, coset=True)
+    assert (y == a).all()
+
+
 def test_domain_interface(ctx):
     d = ozl.poly.Radix2EvaluationDomain.new(ozl.BN254_FR, 1000, ctx=ctx)
     assert d.size() == 1024
