@@ -405,6 +405,7 @@ def run_ours(args):
         "gpu_launches": int(launches_timed),
         "roofline": {"kernel": "k_accumulate", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get((int(math.log2(n)), c, info["factor"])),
+                     "traffic_unit": "bytes per launch",
                      "traffic_source": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01b_ncu_k_accumulate_2p26.csv (one gather of 96 B per point per window, at 64-byte DRAM granularity)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": acc,
