@@ -171,6 +171,22 @@ def cpu_msm_throughput(log_sample: int, steps: int, warmup: int, seed: int = 1):
     return n / dt, dt, threads, c
 
 
+def _stdout_to_stderr():
+    """Point file descriptor 1 at stderr for the duration of a run: libraries that write to stdout
+    from native code (NCCL prints its version line there when NCCL_DEBUG is set) must not share it
+    with the ONE JSON line the driver parses.  Returns the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _restore_stdout(saved):
+    sys.stdout.flush()
+    os.dup2(saved, 1)
+    os.close(saved)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -189,7 +205,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -420,7 +436,7 @@ def run_ours(args):
         v, dt, threads, cc = cpu_msm_throughput(args.cpu_log_n, 1, 0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"one MSM over 2^{args.cpu_log_n} of the workload's points (ark window c={cc}), {dt:.1f} s"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -521,7 +537,7 @@ def run_groth16(args):
                 "d2h_bytes_per_step": 64 + 128 + 64, "api": "ozl_groth16_prove (C ABI, pinned host witness)"},
         "gpu_launches": int(launches), "stages_ms": stages, "verified": verified, "concurrent": conc,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     pk.free()
 
 
@@ -580,7 +596,7 @@ def run_ntt(args):
                      "field_mul_per_s": (n / 2) * log_n / (ms * 1e-3), "measured_mul_peak_per_s": mul_peak,
                      "frac": (n / 2) * log_n / (ms * 1e-3) / mul_peak},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -601,14 +617,33 @@ def main():
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.workload == "groth16":
-        run_groth16(args)
-    elif args.workload == "ntt":
-        run_ntt(args)
-    elif args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    global _SAVED_STDOUT
+    _SAVED_STDOUT = _stdout_to_stderr()
+    try:
+        if args.workload == "groth16":
+            run_groth16(args)
+        elif args.workload == "ntt":
+            run_ntt(args)
+        elif args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        if _SAVED_STDOUT is not None:
+            _restore_stdout(_SAVED_STDOUT)
+            _SAVED_STDOUT = None
+
+
+_SAVED_STDOUT = None
+
+
+def emit(line: dict):
+    """Print the JSON line on the real stdout (restored first if a run redirected it)."""
+    global _SAVED_STDOUT
+    if _SAVED_STDOUT is not None:
+        _restore_stdout(_SAVED_STDOUT)
+        _SAVED_STDOUT = None
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -60,3 +60,23 @@ def test_no_device_fails_loudly():
         pytest.skip("GPU present: covered by -m gpu tests")
     with pytest.raises(openzl_b200.OzlError):
         openzl_b200.Context(0)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on
+    stdout with the contract's keys, whatever native code writes to file descriptor 1 meanwhile."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-log-n", "12"],
+                       capture_output=True, text=True, cwd=root, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config", "cpu_baseline", "e2e"):
+        assert k in d
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0
