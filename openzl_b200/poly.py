@@ -15,6 +15,11 @@ from . import _lib
 from .context import Context
 
 _TWO_ADICITY = {_lib.BN254_FR: 28, _lib.BLS12_381_FR: 32}
+# ark `FftParameters` / `FpParameters` of the two scalar fields: modulus and multiplicative generator
+# (TWO_ADIC_ROOT_OF_UNITY = GENERATOR^((r - 1) / 2^TWO_ADICITY)); the device NTT uses the same constants.
+_MODULUS = {_lib.BN254_FR: 21888242871839275222246405745257275088548364400416034343698204186575808495617,
+            _lib.BLS12_381_FR: 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001}
+_GENERATOR = {_lib.BN254_FR: 5, _lib.BLS12_381_FR: 7}
 
 
 class Radix2EvaluationDomain:
@@ -38,6 +43,73 @@ class Radix2EvaluationDomain:
 
     def size(self) -> int:
         return self._size
+
+    # ---- domain constants and the O(1) / O(n) host-side helpers of the trait ----------------
+    # Returned as canonical Python integers (``Fr::into_repr()``); they parameterise setup-time
+    # formulas, not the per-proof hot path.
+    @property
+    def modulus(self) -> int:
+        return _MODULUS[self.field]
+
+    @property
+    def group_gen(self) -> int:
+        """omega: ``TWO_ADIC_ROOT_OF_UNITY ^ (2^(TWO_ADICITY - log_size_of_group))``."""
+        p = self.modulus
+        w = pow(_GENERATOR[self.field], (p - 1) >> _TWO_ADICITY[self.field], p)
+        for _ in range(_TWO_ADICITY[self.field] - self.log_size_of_group):
+            w = (w * w) % p
+        return w
+
+    @property
+    def group_gen_inv(self) -> int:
+        return pow(self.group_gen, -1, self.modulus)
+
+    @property
+    def size_inv(self) -> int:
+        return pow(self._size, -1, self.modulus)
+
+    @property
+    def generator_inv(self) -> int:
+        """Inverse of ``F::multiplicative_generator()``, the coset shift."""
+        return pow(_GENERATOR[self.field], -1, self.modulus)
+
+    def element(self, i: int) -> int:
+        """``domain.element(i)`` = omega^i."""
+        return pow(self.group_gen, i, self.modulus)
+
+    def elements(self):
+        p, w, cur = self.modulus, self.group_gen, 1
+        for _ in range(self._size):
+            yield cur
+            cur = (cur * w) % p
+
+    def evaluate_vanishing_polynomial(self, tau: int) -> int:
+        """Z(tau) = tau^size - 1."""
+        return (pow(tau, self._size, self.modulus) - 1) % self.modulus
+
+    def evaluate_all_lagrange_coefficients(self, tau: int):
+        """L_i(tau) for all i: Z(tau) * omega^i / (size * (tau - omega^i)); when tau is in the
+        domain the indicator vector, as ark returns."""
+        p, n = self.modulus, self._size
+        z = self.evaluate_vanishing_polynomial(tau)
+        if z == 0:
+            return [1 if e == tau % p else 0 for e in self.elements()]
+        # one batched inversion (Montgomery's trick) for the n denominators
+        dens = [(n * (tau - e)) % p for e in self.elements()]
+        pref, acc = [], 1
+        for d in dens:
+            pref.append(acc)
+            acc = (acc * d) % p
+        inv = pow(acc, -1, p)
+        out = [0] * n
+        for i in range(n - 1, -1, -1):
+            out[i] = (inv * pref[i]) % p
+            inv = (inv * dens[i]) % p
+        cur, w = 1, self.group_gen
+        for i in range(n):
+            out[i] = (out[i] * z % p) * cur % p
+            cur = (cur * w) % p
+        return out
 
     def _prep(self, a: np.ndarray) -> np.ndarray:
         a = np.asarray(a, dtype=np.uint64)
