@@ -81,6 +81,11 @@ def test_prove_matches_oracle_and_verifies(ctx, links):
         for name, k, got in (("bn254_g1", A, proof.a), ("bn254_g2", B, proof.b), ("bn254_g1", C, proof.c)):
             exp, exp_inf = cbind.to_affine(name, cbind.gen_mul(name, k))
             assert not exp_inf and (got == exp).all(), name
+        # ProofSystem::verify (groth16.rs:460-466) with real pairings on the device's proof points
+        if links == 1:
+            from tests.util import verify_proof_with_pairings
+            assert verify_proof_with_pairings("bn254", "bn254_fr", r1, td, [z[1]], proof.a, proof.b, proof.c)
+            assert not verify_proof_with_pairings("bn254", "bn254_fr", r1, td, [(z[1] + 1) % P], proof.a, proof.b, proof.c)
         # wire format (groth16.rs:98-107): 128 compressed bytes that decode back to the same three points
         from openzl_b200 import serialize as ser
         raw = proof.to_bytes("bn254")
@@ -123,6 +128,9 @@ def test_prove_bls12_381(ctx):
         for name, k, got in (("bls12_381_g1", A, proof.a), ("bls12_381_g2", B, proof.b), ("bls12_381_g1", C, proof.c)):
             exp, exp_inf = cbind.to_affine(name, cbind.gen_mul(name, k))
             assert not exp_inf and (got == exp).all(), name
+        # and the device's proof verifies with real pairings (oracle/pairing.py), like ProofSystem::verify
+        from tests.util import verify_proof_with_pairings
+        assert verify_proof_with_pairings("bls12_381", "bls12_381_fr", r1, td, [z[1]], proof.a, proof.b, proof.c)
     finally:
         pk.free()
 
