@@ -72,7 +72,8 @@ const char* ozl_strerror(int status);
 /* Text of the most recent CUDA error seen by this context (empty string if none). */
 const char* ozl_last_error(const ozl_ctx* ctx);
 
-/* One context per (device, stream).  Creates its own non-blocking stream. */
+/* One context per (device, stream).  Creates its own non-blocking stream.  OZL_ERR_NO_DEVICE unless
+ * `device` is a compute-capability-10.x GPU (the library contains sm_100a code only). */
 int ozl_ctx_create(int device, ozl_ctx** out);
 void ozl_ctx_destroy(ozl_ctx* ctx);
 /* Run on a caller-supplied cudaStream_t (passed as void*), e.g. torch's current stream, so the
@@ -107,7 +108,18 @@ int ozl_msm_bases_download(ozl_ctx* ctx, uint32_t handle, size_t first, size_t n
 int ozl_msm_bases_free(ozl_ctx* ctx, uint32_t handle);
 
 /* sum_{i<n} scalars[i] * bases[i] over the first n bases of `handle` (n <= uploaded count,
- * like ark's `size = min(bases.len(), scalars.len())`).  Host scalars in, host Jacobian out. */
+ * like ark's `size = min(bases.len(), scalars.len())`).  Host scalars in, host Jacobian out.
+ * `scalars` may be pageable or page-locked: they cross PCIe in point-range batches while earlier
+ * batches are already being accumulated, so the transfer is hidden under the computation.
+ *
+ * Scalars must be CANONICAL (< r, what `into_repr()` yields).  A scalar with bits the window plan does
+ * not cover (>= 2^255 for BN254, or a recoding carry out of the top window) makes the synchronous
+ * calls (ozl_msm, ozl_msm_sharded) return OZL_ERR_ARG; the *_async / submit forms do not report it.
+ * An all-zero affine base (0, 0) is treated as the point at infinity, with or without `inf_mask`.
+ *
+ * Size limits (32-bit sort entries): n * windows < 2^32 and n * copies < 2^31, where windows =
+ * ceil((scalar bits + 1) / c) and copies is the precompute factor in effect -- e.g. 2^28 points take
+ * at most 7 copies, and 2^29 points with c = 20 (13 windows) are refused with OZL_ERR_ARG. */
 int ozl_msm(ozl_ctx* ctx, uint32_t handle, const uint64_t* scalars, size_t n,
             uint64_t* out_jacobian);
 /* Pipelined form of ozl_msm for back-to-back MSMs (a prover streaming proofs): returns as soon as
@@ -189,6 +201,18 @@ typedef struct {
  * Montgomery).  Used by the setup (transposed matrices) and by tests of the witness map. */
 int ozl_fr_spmv(ozl_ctx* ctx, int field, const ozl_csr* M, const uint64_t* coef_table, uint32_t n_coef,
                 const uint64_t* x, uint32_t n_cols, uint64_t* y);
+
+/* Poseidon permutation over the pairing's scalar field, `batch` states of `width` elements each, in
+ * place (host buffers, Montgomery): the hash of the reference's Groth16 workload circuit
+ * (/root/reference/openzl-crypto/src/poseidon/mod.rs:156-283; S-box x^5,
+ * /root/reference/plugins/arkworks/src/poseidon/mod.rs:147-159).  round_keys = (full_rounds +
+ * partial_rounds) x width elements, round-major; mds = width x width, row-major.  Evaluates hash-chain
+ * witnesses on the device; with the reference's width-3 known-answer vector
+ * (/root/reference/openzl-tutorials/src/poseidon.rs:388-401) it pins the device multiplier directly.
+ * width in 2..12, full_rounds even. */
+int ozl_fr_poseidon_permute(ozl_ctx* ctx, int field, uint64_t* states, size_t batch, uint32_t width,
+                            uint32_t full_rounds, uint32_t partial_rounds, const uint64_t* round_keys,
+                            const uint64_t* mds);
 
 /* out_affine[j] = [scalars[j]] G for the curve's generator G; identity_flags[j] = 1 for the point
  * at infinity.  The fixed-base work of a (known-trapdoor) Groth16 setup. */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libozl_b200.so")
 
 OZL_OK = 0
 STATUS_NAMES = {0: "OZL_OK", 1: "OZL_ERR_ARG", 2: "OZL_ERR_CUDA", 3: "OZL_ERR_NO_DEVICE", 4: "OZL_ERR_OOM",
-                5: "OZL_ERR_HANDLE", 6: "OZL_ERR_DOMAIN"}
+                5: "OZL_ERR_HANDLE", 6: "OZL_ERR_DOMAIN", 7: "OZL_ERR_NCCL"}
 
 # enum ozl_curve / ozl_field (include/ozl.h)
 BLS12_381_G1, BLS12_381_G2, BN254_G1, BN254_G2 = 0, 1, 2, 3
@@ -28,7 +28,7 @@ EXPORTS = [
     "ozl_msm_bases_upload_device", "ozl_msm_bases_generate", "ozl_msm_bases_precompute", "ozl_msm_bases_download", "ozl_msm_bases_free",
     "ozl_msm", "ozl_msm_submit", "ozl_msm_device_async", "ozl_msm_set_window_bits", "ozl_msm_set_batch_affine", "ozl_msm_get_window_bits", "ozl_msm_bases_info", "ozl_jacobian_sum",
     "ozl_jacobian_to_affine", "ozl_ntt", "ozl_ntt_device_async", "ozl_ctx_enable_timing",
-    "ozl_ctx_get_stage_times", "ozl_ctx_launch_count", "ozl_bench_field_mul", "ozl_fr_spmv", "ozl_fixed_base_mul",
+    "ozl_ctx_get_stage_times", "ozl_ctx_launch_count", "ozl_bench_field_mul", "ozl_fr_spmv", "ozl_fr_poseidon_permute", "ozl_fixed_base_mul",
     "ozl_groth16_pk_create", "ozl_groth16_pk_destroy", "ozl_groth16_prove", "ozl_groth16_domain_size",
     "ozl_comm_unique_id", "ozl_comm_create", "ozl_comm_destroy", "ozl_msm_sharded", "ozl_msm_sharded_device_async",
     "ozl_comm_allgather_sum_async",
@@ -119,6 +119,7 @@ def load() -> ctypes.CDLL:
     csrp = ctypes.POINTER(Csr)
     u32 = ctypes.c_uint32
     lib.ozl_fr_spmv.argtypes = [vp, ctypes.c_int, csrp, vp, u32, vp, u32, vp]
+    lib.ozl_fr_poseidon_permute.argtypes = [vp, ctypes.c_int, vp, sz, u32, u32, u32, vp, vp]
     lib.ozl_fixed_base_mul.argtypes = [vp, ctypes.c_int, vp, sz, vp, vp]
     lib.ozl_groth16_pk_create.argtypes = [vp, ctypes.c_int, u32, u32, u32, csrp, csrp, csrp, vp, u32, u32, u32, u32, u32, u32,
                                           vp, vp, vp, vp, vp, u32p]

@@ -34,12 +34,71 @@ int alloc_bases(ozl_ctx* ctx, int curve, size_t n, bool with_inf, Bases* b) {
   b->n = n;
   CUDA_TRY(ctx, cudaMalloc((void**)&b->d_pts, std::max<size_t>(n, 1) * 2 * cu * 4));
   if (with_inf) {
-    cudaError_t e = cudaMalloc((void**)&b->d_inf, (n + 7) / 8 + 1);
+    const size_t bytes = (((n + 7) / 8 + 3) & ~(size_t)3) + 4;   // whole 32-bit words (k_mark_zero_points ORs words)
+    cudaError_t e = cudaMalloc((void**)&b->d_inf, bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_inf, 0, bytes, ctx->stream);
     if (e != cudaSuccess) {
       cudaFree(b->d_pts);
+      if (b->d_inf) cudaFree(b->d_inf);
+      b->d_pts = nullptr;
+      b->d_inf = nullptr;
       ctx->last_error = cudaGetErrorString(e);
       return OZL_ERR_OOM;
     }
+  }
+  return OZL_OK;
+}
+
+void release_bases(Bases& b) {
+  if (b.d_pts) cudaFree(b.d_pts);
+  if (b.d_inf) cudaFree(b.d_inf);
+  b.d_pts = nullptr;
+  b.d_inf = nullptr;
+}
+
+// An all-zero affine point is not on any of the curves (b != 0): ark never produces it, but a caller that
+// encodes GroupAffine::infinity as (0, 0) without an inf_mask means the identity.  Marking such points
+// in the bitset at upload time makes every path treat them alike (skipped at digit extraction), with
+// and without precomputed copies.
+__global__ void k_mark_zero_points(const uint32_t* __restrict__ pts, uint32_t n, int aff_words, uint32_t* __restrict__ inf_words) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* p = reinterpret_cast<const uint4*>(pts + (size_t)i * aff_words);
+  uint32_t t = 0;
+  for (int k = 0; k < aff_words / 4; k++) {
+    const uint4 v = p[k];
+    t |= v.x | v.y | v.z | v.w;
+  }
+  if (t == 0) atomicOr(&inf_words[i >> 5], 1u << (i & 31));
+}
+
+int finish_upload(ozl_ctx* ctx, Bases& b, uint32_t* handle) {
+  if (b.n) {
+    k_mark_zero_points<<<(unsigned)((b.n + 255) / 256), 256, 0, ctx->stream>>>(b.d_pts, (uint32_t)b.n, 2 * coord_u32(b.curve), (uint32_t*)b.d_inf);
+    ctx->launches++;
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("bases_upload: ") + cudaGetErrorString(e);
+    release_bases(b);
+    return OZL_ERR_CUDA;
+  }
+  *handle = ctx->next_handle++;
+  ctx->bases[*handle] = b;
+  return OZL_OK;
+}
+
+// D2H of the result and of the input-error flags, then the verdict of a synchronous MSM call
+int finish_msm(ozl_ctx* ctx, const Bases& b, uint64_t* out_jacobian) {
+  const size_t out_bytes = 3 * coord_u32(b.curve) * 4;
+  uint32_t flags = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_jacobian, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(&flags, msm_err_flags(ctx->ws), 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flags & 1u) {
+    ctx->last_error = "msm: a scalar has bits above the window plan (scalars must be canonical, i.e. reduced modulo r)";
+    return OZL_ERR_ARG;
   }
   return OZL_OK;
 }
@@ -78,7 +137,11 @@ int ozl_ctx_create(int device, ozl_ctx** out) {
   if (!ctx) return OZL_ERR_OOM;
   ctx->device = device;
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    delete ctx;   // the library holds sm_100a code only: anything but a Blackwell data-centre part cannot run it
+    return OZL_ERR_NO_DEVICE;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return OZL_ERR_CUDA;
@@ -93,6 +156,14 @@ void ozl_ctx_destroy(ozl_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   stages_clear(ctx);
+  if (ctx->pk_deleter) {
+    std::map<uint32_t, ozl_rt::Groth16Pk*> pks;
+    pks.swap(ctx->pks);
+    for (auto& kv : pks) ctx->pk_deleter(ctx, kv.second);   // frees the pk's device buffers and its five bases handles
+  }
+  for (cudaEvent_t e : ctx->ev_batch)
+    if (e) cudaEventDestroy(e);
+  if (ctx->ev_prior) cudaEventDestroy(ctx->ev_prior);
   for (auto& kv : ctx->bases) {
     cudaFree(kv.second.d_pts);
     if (kv.second.d_inf) cudaFree(kv.second.d_inf);
@@ -142,34 +213,40 @@ int ozl_curve_coord_limbs(int curve) { return coord_u32(curve) / 2; }
 // ---- bases ----------------------------------------------------------------------------------
 int ozl_msm_bases_upload(ozl_ctx* ctx, int curve, const uint64_t* bases, const uint8_t* inf_mask, size_t n,
                          uint32_t* handle) {
-  if (!ctx || !handle || (!bases && n)) return OZL_ERR_ARG;
+  if (!ctx || !handle || (!bases && n) || n >= 0x7fffffffull) return OZL_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   Bases b;
-  int r = alloc_bases(ctx, curve, n, inf_mask != nullptr, &b);
+  int r = alloc_bases(ctx, curve, n, true, &b);
   if (r) return r;
   const size_t bytes = n * 2 * coord_u32(curve) * 4;
-  CUDA_TRY(ctx, cudaMemcpyAsync(b.d_pts, bases, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (inf_mask) CUDA_TRY(ctx, cudaMemcpyAsync(b.d_inf, inf_mask, (n + 7) / 8, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  *handle = ctx->next_handle++;
-  ctx->bases[*handle] = b;
-  return OZL_OK;
+  cudaError_t e = cudaMemcpyAsync(b.d_pts, bases, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && inf_mask) e = cudaMemcpyAsync(b.d_inf, inf_mask, (n + 7) / 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("bases_upload: ") + cudaGetErrorString(e);
+    cudaStreamSynchronize(ctx->stream);
+    release_bases(b);
+    return OZL_ERR_CUDA;
+  }
+  return finish_upload(ctx, b, handle);
 }
 
 int ozl_msm_bases_upload_device(ozl_ctx* ctx, int curve, const uint64_t* d_bases, const uint8_t* d_inf_mask, size_t n,
                                 uint32_t* handle) {
-  if (!ctx || !handle || (!d_bases && n)) return OZL_ERR_ARG;
+  if (!ctx || !handle || (!d_bases && n) || n >= 0x7fffffffull) return OZL_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   Bases b;
-  int r = alloc_bases(ctx, curve, n, d_inf_mask != nullptr, &b);
+  int r = alloc_bases(ctx, curve, n, true, &b);
   if (r) return r;
   const size_t bytes = n * 2 * coord_u32(curve) * 4;
-  CUDA_TRY(ctx, cudaMemcpyAsync(b.d_pts, d_bases, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-  if (d_inf_mask) CUDA_TRY(ctx, cudaMemcpyAsync(b.d_inf, d_inf_mask, (n + 7) / 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  *handle = ctx->next_handle++;
-  ctx->bases[*handle] = b;
-  return OZL_OK;
+  cudaError_t e = cudaMemcpyAsync(b.d_pts, d_bases, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess && d_inf_mask) e = cudaMemcpyAsync(b.d_inf, d_inf_mask, (n + 7) / 8, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("bases_upload_device: ") + cudaGetErrorString(e);
+    cudaStreamSynchronize(ctx->stream);
+    release_bases(b);
+    return OZL_ERR_CUDA;
+  }
+  return finish_upload(ctx, b, handle);
 }
 
 int ozl_msm_bases_generate(ozl_ctx* ctx, int curve, uint64_t start, size_t n, uint32_t* handle) {
@@ -275,17 +352,11 @@ int ozl_msm(ozl_ctx* ctx, uint32_t handle, const uint64_t* scalars, size_t n, ui
   if (r) return r;
   if (n > b->n) return OZL_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const size_t out_bytes = 3 * coord_u32(b->curve) * 4;
-  if ((r = ensure(ctx, ctx->scalars, std::max<size_t>(n, 1) * 32))) return r;
   if ((r = ensure(ctx, ctx->out, 1024))) return r;
   if (ctx->timing) stages_clear(ctx);
-  STAGE(ctx, "h2d_scalars");
-  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  STAGE_END(ctx);
-  if ((r = msm_dispatch(ctx, *b, (const uint32_t*)ctx->scalars.p, n, (uint32_t*)ctx->out.p))) return r;
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_jacobian, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  return OZL_OK;
+  // scalars cross PCIe in point-range batches while earlier batches are already being accumulated
+  if ((r = ozl_rt_msm_host(ctx, *b, scalars, n, (uint32_t*)ctx->out.p))) return r;
+  return finish_msm(ctx, *b, out_jacobian);
 }
 
 int ozl_msm_submit(ozl_ctx* ctx, uint32_t handle, const uint64_t* scalars, size_t n, uint64_t* out_jacobian) {

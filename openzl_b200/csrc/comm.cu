@@ -144,17 +144,26 @@ int ozl_msm_sharded(ozl_ctx* ctx, ozl_comm* c, uint32_t handle, const uint64_t* 
   if (!ctx || !c || c->ctx != ctx || !out_jacobian || (!scalars && n)) return OZL_ERR_ARG;
   auto it = ctx->bases.find(handle);
   if (it == ctx->bases.end()) return OZL_ERR_HANDLE;
-  const int curve = it->second.curve;
-  if (n > it->second.n) return OZL_ERR_ARG;
+  const Bases& b = it->second;
+  const int curve = b.curve;
+  if (n > b.n) return OZL_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t out_bytes = 3 * (size_t)coord_u32(curve) * 4;
   int r;
-  if ((r = ensure(ctx, ctx->scalars, std::max<size_t>(n, 1) * 32))) return r;
   if ((r = ensure(ctx, ctx->out, 1024))) return r;
-  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  if ((r = ozl_msm_sharded_device_async(ctx, c, handle, (const uint64_t*)ctx->scalars.p, n, (uint64_t*)ctx->out.p))) return r;
+  if (ctx->timing) stages_clear(ctx);
+  // shard MSM with the host->device copy of the shard's scalars hidden under the accumulation
+  // (batches, runtime.cuh: ozl_rt_msm_host), then the all-gather + sum, all stream-ordered
+  if ((r = ozl_rt_msm_host(ctx, b, scalars, n, (uint32_t*)ctx->out.p))) return r;
+  if ((r = ozl_comm_allgather_sum_async(ctx, c, curve, (const uint64_t*)ctx->out.p, (uint64_t*)ctx->out.p))) return r;
+  uint32_t flags = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(out_jacobian, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(&flags, msm_err_flags(ctx->ws), 4, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flags & 1u) {
+    ctx->last_error = "msm_sharded: a scalar has bits above the window plan (scalars must be canonical)";
+    return OZL_ERR_ARG;
+  }
   return OZL_OK;
 }
 

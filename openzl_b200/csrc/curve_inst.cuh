@@ -9,6 +9,10 @@ int msm_entry(ozl_ctx* ctx, ozl_rt::MsmWorkspace& ws, cudaStream_t st, const ozl
               size_t n, uint32_t* d_out) {
   return ozl_rt::msm_run<F_>(ctx, ws, st, b, d_scalars, n, d_out);
 }
+int msm_batched_entry(ozl_ctx* ctx, ozl_rt::MsmWorkspace& ws, cudaStream_t st, const ozl_rt::Bases& b, const uint32_t* d_scalars,
+                      size_t n, const ozl_rt::MsmBatches& mb, uint32_t* d_out) {
+  return ozl_rt::msm_run_batched<F_>(ctx, ws, st, b, d_scalars, n, mb, d_out);
+}
 void generate_entry(cudaStream_t st, uint64_t start, uint32_t n, uint32_t* d_pts) {
   const uint32_t threads = (n + GEN_RUN - 1) / GEN_RUN;
   k_generate_bases<F_, C_><<<(threads + 127) / 128, 128, 0, st>>>(start, n, d_pts);
@@ -46,4 +50,4 @@ void a2j_entry(cudaStream_t st, const uint32_t* d_aff, uint32_t* d_out) {
 }
 }  // namespace
 
-const OzlCurveOps OZL_OPS = {msm_entry, generate_entry, jsum_entry, jaff_entry, bench_entry, fixed_base_entry, lincomb_entry, smul_var_entry, smul_table_entry, build_table_entry, precompute_entry, a2j_entry};
+const OzlCurveOps OZL_OPS = {msm_entry, msm_batched_entry, generate_entry, jsum_entry, jaff_entry, bench_entry, fixed_base_entry, lincomb_entry, smul_var_entry, smul_table_entry, build_table_entry, precompute_entry, a2j_entry};

@@ -9,6 +9,7 @@ struct ozl_ctx;
 namespace ozl_rt {
 struct Bases;
 struct MsmWorkspace;
+struct MsmBatches;
 }
 namespace ozl {
 struct NttWorkspace;
@@ -17,6 +18,9 @@ struct NttWorkspace;
 struct OzlCurveOps {
   int (*msm)(ozl_ctx* ctx, ozl_rt::MsmWorkspace& ws, cudaStream_t st, const ozl_rt::Bases& b, const uint32_t* d_scalars,
              size_t n, uint32_t* d_out);
+  // same MSM with the scalars arriving in point-range batches (host->device copy overlapped with the accumulation)
+  int (*msm_batched)(ozl_ctx* ctx, ozl_rt::MsmWorkspace& ws, cudaStream_t st, const ozl_rt::Bases& b, const uint32_t* d_scalars,
+                     size_t n, const ozl_rt::MsmBatches& mb, uint32_t* d_out);
   void (*generate)(cudaStream_t st, uint64_t start, uint32_t n, uint32_t* d_pts);
   void (*jacobian_sum)(cudaStream_t st, const uint32_t* d_pts, uint32_t k, uint32_t* d_out);
   void (*jacobian_to_affine)(cudaStream_t st, const uint32_t* d_jac, uint32_t* d_out, int* d_flag);
@@ -50,6 +54,9 @@ struct OzlFieldOps {
   void (*vanishing_inv)(cudaStream_t st, int log_n, uint32_t* out);
   // out = a * b mod r, all canonical 256-bit integers on the device
   void (*mul_canonical)(cudaStream_t st, const uint32_t* a, const uint32_t* b, uint32_t* out);
+  // Poseidon permutation of `batch` states of `width` elements in place (Montgomery), x^5 S-box
+  void (*poseidon)(cudaStream_t st, uint32_t* states, uint32_t batch, int width, int full_rounds, int partial_rounds,
+                   const uint32_t* round_keys, const uint32_t* mds);
 };
 extern const OzlFieldOps ozl_fops_bn254_fr;
 extern const OzlFieldOps ozl_fops_bls12_381_fr;

@@ -36,19 +36,22 @@ struct XYZZ {
 
   OZL_DEV XYZZ neg() const { XYZZ r = *this; r.y = y.neg(); return r; }
 
+  // The cold-path formulas below issue their field products in independent PAIRS through
+  // F::mul2_ni / F::sqr2_ni (one out-of-line body, two interleaved carry chains): the kernels that
+  // use them run few warps per SM and are bound by dependent-issue latency, not by pipe throughput.
+
   // 2 * (affine p), mdbl-2008-s with a = 0
   static OZL_DEV_NOINLINE XYZZ dbl_affine(const Affine<F>& p) {
     XYZZ r;
     F u = p.y.dbl();
-    F v = F::sqr_ni(u);
-    F w = F::mul_ni(u, v);
-    F s = F::mul_ni(p.x, v);
-    F xx = F::sqr_ni(p.x);
-    F m = xx.dbl() + xx;
-    r.x = F::sqr_ni(m) - s.dbl();
-    r.y = F::mul_ni(m, s - r.x) - F::mul_ni(w, p.y);
-    r.zz = v;
-    r.zzz = w;
+    typename F::Pair a = F::sqr2_ni(u, p.x);              // v = u^2, xx = x^2
+    F m = a.b.dbl() + a.b;
+    typename F::Pair b = F::mul2_ni(u, a.a, p.x, a.a);    // w = u v, s = x v
+    typename F::Pair c = F::mul2_ni(m, m, b.a, p.y);      // m^2, w y
+    r.x = c.a - b.b.dbl();
+    r.y = F::mul_ni(m, b.b - r.x) - c.b;
+    r.zz = a.a;
+    r.zzz = b.a;
     return r;
   }
 
@@ -57,15 +60,15 @@ struct XYZZ {
     if (is_identity()) return *this;
     XYZZ r;
     F u = y.dbl();
-    F v = F::sqr_ni(u);
-    F w = F::mul_ni(u, v);
-    F s = F::mul_ni(x, v);
-    F xx = F::sqr_ni(x);
-    F m = xx.dbl() + xx;
-    r.x = F::sqr_ni(m) - s.dbl();
-    r.y = F::mul_ni(m, s - r.x) - F::mul_ni(w, y);
-    r.zz = F::mul_ni(v, zz);
-    r.zzz = F::mul_ni(w, zzz);
+    typename F::Pair a = F::sqr2_ni(u, x);                // v = u^2, xx = x^2
+    F m = a.b.dbl() + a.b;
+    typename F::Pair b = F::mul2_ni(u, a.a, x, a.a);      // w = u v, s = x v
+    typename F::Pair c = F::mul2_ni(m, m, b.a, y);        // m^2, w y
+    r.x = c.a - b.b.dbl();
+    typename F::Pair d = F::mul2_ni(m, b.b - r.x, a.a, zz);
+    r.y = d.a - c.b;
+    r.zz = d.b;
+    r.zzz = F::mul_ni(b.a, zzz);
     return r;
   }
 
@@ -103,10 +106,9 @@ struct XYZZ {
       *this = from_affine(p);
       return;
     }
-    F u2 = F::mul_ni(p.x, zz);
-    F s2 = F::mul_ni(p.y, zzz);
-    F pp = u2 - x;
-    F r = s2 - y;
+    typename F::Pair a = F::mul2_ni(p.x, zz, p.y, zzz);   // u2, s2
+    F pp = a.a - x;
+    F r = a.b - y;
     if (pp.is_zero()) {
       if (r.is_zero()) {
         *this = dbl_affine(p);
@@ -115,14 +117,15 @@ struct XYZZ {
       }
       return;
     }
-    F p2 = F::sqr_ni(pp);
-    F p3 = F::mul_ni(pp, p2);
-    F q = F::mul_ni(x, p2);
-    F x3 = F::sqr_ni(r) - p3 - q.dbl();
-    y = F::mul_ni(r, q - x3) - F::mul_ni(y, p3);
+    typename F::Pair b = F::sqr2_ni(pp, r);               // p2, r^2
+    typename F::Pair c = F::mul2_ni(pp, b.a, x, b.a);     // p3, q
+    F x3 = b.b - c.a - c.b.dbl();
+    typename F::Pair d = F::mul2_ni(r, c.b - x3, y, c.a);
+    typename F::Pair e = F::mul2_ni(zz, b.a, zzz, c.a);
+    y = d.a - d.b;
     x = x3;
-    zz = F::mul_ni(zz, p2);
-    zzz = F::mul_ni(zzz, p3);
+    zz = e.a;
+    zzz = e.b;
   }
 
   // this += o (add-2008-s)
@@ -132,12 +135,10 @@ struct XYZZ {
       *this = o;
       return;
     }
-    F u1 = F::mul_ni(x, o.zz);
-    F u2 = F::mul_ni(o.x, zz);
-    F s1 = F::mul_ni(y, o.zzz);
-    F s2 = F::mul_ni(o.y, zzz);
-    F pp = u2 - u1;
-    F r = s2 - s1;
+    typename F::Pair u = F::mul2_ni(x, o.zz, o.x, zz);    // u1, u2
+    typename F::Pair s = F::mul2_ni(y, o.zzz, o.y, zzz);  // s1, s2
+    F pp = u.b - u.a;
+    F r = s.b - s.a;
     if (pp.is_zero()) {
       if (r.is_zero()) {
         *this = dbl();
@@ -146,14 +147,16 @@ struct XYZZ {
       }
       return;
     }
-    F p2 = F::sqr_ni(pp);
-    F p3 = F::mul_ni(pp, p2);
-    F q = F::mul_ni(u1, p2);
-    F x3 = F::sqr_ni(r) - p3 - q.dbl();
-    y = F::mul_ni(r, q - x3) - F::mul_ni(s1, p3);
+    typename F::Pair b = F::sqr2_ni(pp, r);               // p2, r^2
+    typename F::Pair c = F::mul2_ni(pp, b.a, u.a, b.a);   // p3, q
+    F x3 = b.b - c.a - c.b.dbl();
+    typename F::Pair d = F::mul2_ni(r, c.b - x3, s.a, c.a);
+    typename F::Pair z = F::mul2_ni(zz, o.zz, zzz, o.zzz);
+    typename F::Pair e = F::mul2_ni(z.a, b.a, z.b, c.a);
+    y = d.a - d.b;
     x = x3;
-    zz = F::mul_ni(F::mul_ni(zz, o.zz), p2);
-    zzz = F::mul_ni(F::mul_ni(zzz, o.zzz), p3);
+    zz = e.a;
+    zzz = e.b;
   }
 
   // [k] * this for a small unsigned k (left-to-right double-and-add); cold path.

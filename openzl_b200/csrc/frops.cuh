@@ -71,4 +71,44 @@ __global__ void k_mul_canonical(const uint32_t* __restrict__ a, const uint32_t* 
   for (int i = 0; i < F::N; i++) out[i] = r.v[i];
 }
 
+// Poseidon permutation, one state per thread: the workload hash of the Groth16 benchmark circuit
+// (/root/reference/openzl-crypto/src/poseidon/mod.rs:156-283: a round adds the round keys, applies the
+// S-box x^5 -- to every element in the R_F/2 leading and trailing full rounds, to element 0 in the R_P
+// partial rounds between them -- and multiplies by the MDS matrix, row-major, next[i] = sum_j mds[i][j] state[j];
+// S-box at /root/reference/plugins/arkworks/src/poseidon/mod.rs:147-159).  Evaluates witnesses for
+// batches of hashes on the device and pins the device's Montgomery arithmetic to the reference's
+// width-3 known-answer test (tests/test_gpu_poseidon.py).
+static constexpr int POSEIDON_MAX_WIDTH = 12;   // the reference tabulates MDS matrices for widths 2..12
+
+template <class P>
+__global__ void __launch_bounds__(128)
+k_poseidon_permute(uint32_t* __restrict__ states, uint32_t batch, int width, int full_rounds, int partial_rounds,
+                   const uint32_t* __restrict__ round_keys, const uint32_t* __restrict__ mds) {
+  typedef Fp<P> F;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  F st[POSEIDON_MAX_WIDTH], nx[POSEIDON_MAX_WIDTH];
+  uint32_t* mine = states + (size_t)i * width * F::N;
+  for (int k = 0; k < width; k++) st[k] = F::load(mine + k * F::N);
+  const int half = full_rounds / 2;
+  for (int rnd = 0; rnd < full_rounds + partial_rounds; rnd++) {
+    const bool full = rnd < half || rnd >= half + partial_rounds;
+    for (int k = 0; k < width; k++) {
+      F v = st[k] + F::load(round_keys + ((size_t)rnd * width + k) * F::N);
+      if (full || k == 0) {
+        const F v2 = F::mul_ni(v, v);
+        v = F::mul_ni(F::mul_ni(v2, v2), v);
+      }
+      st[k] = v;
+    }
+    for (int r = 0; r < width; r++) {
+      F acc = F::zero();
+      for (int k = 0; k < width; k++) acc = acc + F::mul_ni(F::load(mds + ((size_t)r * width + k) * F::N), st[k]);
+      nx[r] = acc;
+    }
+    for (int k = 0; k < width; k++) st[k] = nx[k];
+  }
+  for (int k = 0; k < width; k++) st[k].store(mine + k * F::N);
+}
+
 }  // namespace ozl

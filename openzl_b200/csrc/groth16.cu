@@ -7,8 +7,9 @@
 //   C = l_acc + h_acc + s A + r B1 - r s delta  (computed as l + h + s A + r (beta1 + b1_acc)).
 // Everything between the H2D copy of z and the D2H copy of the three proof points stays in HBM.
 #include "runtime.cuh"
+#include "frops.cuh"
 
-namespace {
+namespace ozl_rt {
 
 struct DevCsr {
   uint32_t n_rows = 0;
@@ -38,11 +39,17 @@ struct Groth16Pk {
   MsmWorkspace ws1, ws2;
 };
 
-std::map<uint32_t, Groth16Pk>& pk_registry() {
-  static std::map<uint32_t, Groth16Pk> r;
-  return r;
+}  // namespace ozl_rt
+
+namespace {
+
+// Proving keys live in their context (ozl_ctx::pks): one context per thread is the library's
+// threading model, so the registry needs no lock, a handle cannot be used with a foreign context, and
+// ozl_ctx_destroy releases whatever the caller left behind.
+Groth16Pk* find_pk(ozl_ctx* ctx, uint32_t handle) {
+  auto it = ctx->pks.find(handle);
+  return it == ctx->pks.end() ? nullptr : it->second;
 }
-uint32_t g_next_pk = 1;
 
 void free_csr(DevCsr& m) {
   if (m.row_ptr) cudaFree(m.row_ptr);
@@ -74,17 +81,24 @@ int g1_curve(int pairing) { return pairing == OZL_PAIRING_BN254 ? OZL_BN254_G1 :
 int g2_curve(int pairing) { return pairing == OZL_PAIRING_BN254 ? OZL_BN254_G2 : OZL_BLS12_381_G2; }
 int fr_field(int pairing) { return pairing == OZL_PAIRING_BN254 ? OZL_BN254_FR : OZL_BLS12_381_FR; }
 
-void destroy_pk(ozl_ctx* ctx, Groth16Pk& pk) {
+void destroy_pk(ozl_ctx* ctx, Groth16Pk* pkp) {
+  if (!pkp) return;
+  Groth16Pk& pk = *pkp;
+  cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (pk.s1) cudaStreamSynchronize(pk.s1);
+  if (pk.s2) cudaStreamSynchronize(pk.s2);
   free_csr(pk.A); free_csr(pk.B); free_csr(pk.C);
   void* ptrs[] = {pk.tables_g1, pk.tables_g2, pk.coef, pk.consts_g1, pk.consts_g2, pk.zinv, pk.z, pk.zc, pk.a, pk.b, pk.c, pk.hc, pk.acc, pk.rs};
   for (void* p : ptrs) if (p) cudaFree(p);
-  for (uint32_t h : {pk.h_a, pk.h_b1, pk.h_b2, pk.h_h, pk.h_l}) ozl_msm_bases_free(ctx, h);
+  for (uint32_t h : {pk.h_a, pk.h_b1, pk.h_b2, pk.h_h, pk.h_l})
+    if (h) ozl_msm_bases_free(ctx, h);
   free_workspace(pk.ws1);
   free_workspace(pk.ws2);
   if (pk.s1) cudaStreamDestroy(pk.s1);
   if (pk.s2) cudaStreamDestroy(pk.s2);
   for (cudaEvent_t e : {pk.ev_z, pk.ev_s1, pk.ev_s2}) if (e) cudaEventDestroy(e);
+  delete pkp;
 }
 
 }  // namespace
@@ -114,6 +128,33 @@ int ozl_fr_spmv(ozl_ctx* ctx, int field, const ozl_csr* M, const uint64_t* coef_
   if (e == cudaSuccess) e = cudaGetLastError();
   cleanup();
   if (e != cudaSuccess) { ctx->last_error = std::string("fr_spmv: ") + cudaGetErrorString(e); return OZL_ERR_CUDA; }
+  return OZL_OK;
+}
+
+int ozl_fr_poseidon_permute(ozl_ctx* ctx, int field, uint64_t* states, size_t batch, uint32_t width, uint32_t full_rounds,
+                            uint32_t partial_rounds, const uint64_t* round_keys, const uint64_t* mds) {
+  if (!ctx || !states || !round_keys || !mds) return OZL_ERR_ARG;
+  if (width < 2 || width > (uint32_t)ozl::POSEIDON_MAX_WIDTH || (full_rounds & 1) || full_rounds + partial_rounds == 0 ||
+      full_rounds + partial_rounds > 4096 || batch >= 0x7fffffffull / width) return OZL_ERR_ARG;
+  const OzlFieldOps* f = field_ops(field);
+  if (!f) return OZL_ERR_ARG;
+  if (!batch) return OZL_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t st_bytes = batch * width * 32, rk_bytes = (size_t)(full_rounds + partial_rounds) * width * 32, mds_bytes = (size_t)width * width * 32;
+  uint32_t *ds = nullptr, *dk = nullptr, *dm = nullptr;
+  auto cleanup = [&]() { if (ds) cudaFree(ds); if (dk) cudaFree(dk); if (dm) cudaFree(dm); };
+  if (cudaMalloc((void**)&ds, st_bytes) != cudaSuccess || cudaMalloc((void**)&dk, rk_bytes) != cudaSuccess ||
+      cudaMalloc((void**)&dm, mds_bytes) != cudaSuccess) { cleanup(); cudaGetLastError(); return OZL_ERR_OOM; }
+  cudaMemcpyAsync(ds, states, st_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dk, round_keys, rk_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dm, mds, mds_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  f->poseidon(ctx->stream, ds, (uint32_t)batch, (int)width, (int)full_rounds, (int)partial_rounds, dk, dm);
+  ctx->launches++;
+  cudaMemcpyAsync(states, ds, st_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (e != cudaSuccess) { ctx->last_error = std::string("fr_poseidon_permute: ") + cudaGetErrorString(e); return OZL_ERR_CUDA; }
   return OZL_OK;
 }
 
@@ -147,40 +188,17 @@ int ozl_fixed_base_mul(ozl_ctx* ctx, int curve, const uint64_t* scalars, size_t 
   return OZL_OK;
 }
 
-int ozl_groth16_pk_create(ozl_ctx* ctx, int pairing, uint32_t n_constraints, uint32_t n_instance, uint32_t n_vars,
-                          const ozl_csr* A, const ozl_csr* B, const ozl_csr* C, const uint64_t* coef_table,
-                          uint32_t n_coef, uint32_t a_query, uint32_t b_g1_query, uint32_t b_g2_query,
-                          uint32_t h_query, uint32_t l_query, const uint64_t* alpha_g1, const uint64_t* beta_g1,
-                          const uint64_t* delta_g1, const uint64_t* beta_g2, const uint64_t* delta_g2,
-                          uint32_t* pk_handle) {
-  if (!ctx || !A || !B || !C || !coef_table || !alpha_g1 || !beta_g1 || !delta_g1 || !beta_g2 || !delta_g2 || !pk_handle)
-    return OZL_ERR_ARG;
-  if (pairing != OZL_PAIRING_BN254 && pairing != OZL_PAIRING_BLS12_381) return OZL_ERR_ARG;
-  if (A->n_rows != n_constraints || B->n_rows != n_constraints || C->n_rows != n_constraints) return OZL_ERR_ARG;
-  if (n_instance == 0 || n_instance > n_vars) return OZL_ERR_ARG;
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  Groth16Pk pk;
-  pk.pairing = pairing;
-  pk.n_constraints = n_constraints; pk.n_instance = n_instance; pk.n_vars = n_vars;
-  const uint64_t need = (uint64_t)n_constraints + n_instance;   // ark: domain over num_constraints + num_inputs
-  uint32_t log_n = 0;
-  while (((uint64_t)1 << log_n) < need) log_n++;
-  const int two_adicity = pairing == OZL_PAIRING_BN254 ? 28 : 32;
-  if ((int)log_n > two_adicity || log_n > 30) return OZL_ERR_DOMAIN;
-  pk.log_n = log_n;
+}  // extern "C"
+
+namespace {
+// device-side part of pk_create; any failure leaves *pkp for destroy_pk (the caller keeps its bases handles)
+int pk_build(ozl_ctx* ctx, Groth16Pk* pkp, const ozl_csr* A, const ozl_csr* B, const ozl_csr* C, const uint64_t* coef_table,
+             uint32_t n_coef, const uint64_t* alpha_g1, const uint64_t* beta_g1, const uint64_t* delta_g1,
+             const uint64_t* beta_g2, const uint64_t* delta_g2) {
+  Groth16Pk& pk = *pkp;
+  const int pairing = pk.pairing;
+  const uint32_t n_vars = pk.n_vars, log_n = pk.log_n;
   const size_t n = (size_t)1 << log_n;
-  // handle sanity
-  Bases *ba, *bb1, *bb2, *bh, *bl;
-  for (auto hp : {std::make_pair(a_query, &ba), std::make_pair(b_g1_query, &bb1), std::make_pair(b_g2_query, &bb2),
-                  std::make_pair(h_query, &bh), std::make_pair(l_query, &bl)}) {
-    auto it = ctx->bases.find(hp.first);
-    if (it == ctx->bases.end()) return OZL_ERR_HANDLE;
-    *hp.second = &it->second;
-  }
-  if (ba->curve != g1_curve(pairing) || bb1->curve != g1_curve(pairing) || bh->curve != g1_curve(pairing) ||
-      bl->curve != g1_curve(pairing) || bb2->curve != g2_curve(pairing)) return OZL_ERR_ARG;
-  if (ba->n < n_vars || bb1->n < n_vars || bb2->n < n_vars || bh->n < n - 1 || bl->n < n_vars - n_instance) return OZL_ERR_ARG;
-  pk.h_a = a_query; pk.h_b1 = b_g1_query; pk.h_b2 = b_g2_query; pk.h_h = h_query; pk.h_l = l_query;
   int r;
   if ((r = upload_csr(ctx, A, &pk.A)) || (r = upload_csr(ctx, B, &pk.B)) || (r = upload_csr(ctx, C, &pk.C))) return r;
   const int c1 = coord_u32(g1_curve(pairing)), c2 = coord_u32(g2_curve(pairing));
@@ -229,34 +247,89 @@ int ozl_groth16_pk_create(ozl_ctx* ctx, int pairing, uint32_t n_constraints, uin
   field_ops(fr_field(pairing))->vanishing_inv(ctx->stream, (int)log_n, pk.zinv);
   ctx->launches += 6;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  *pk_handle = g_next_pk++;
-  pk_registry()[*pk_handle] = pk;
+  return OZL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ozl_groth16_pk_create(ozl_ctx* ctx, int pairing, uint32_t n_constraints, uint32_t n_instance, uint32_t n_vars,
+                          const ozl_csr* A, const ozl_csr* B, const ozl_csr* C, const uint64_t* coef_table,
+                          uint32_t n_coef, uint32_t a_query, uint32_t b_g1_query, uint32_t b_g2_query,
+                          uint32_t h_query, uint32_t l_query, const uint64_t* alpha_g1, const uint64_t* beta_g1,
+                          const uint64_t* delta_g1, const uint64_t* beta_g2, const uint64_t* delta_g2,
+                          uint32_t* pk_handle) {
+  if (!ctx || !A || !B || !C || !coef_table || !alpha_g1 || !beta_g1 || !delta_g1 || !beta_g2 || !delta_g2 || !pk_handle)
+    return OZL_ERR_ARG;
+  if (pairing != OZL_PAIRING_BN254 && pairing != OZL_PAIRING_BLS12_381) return OZL_ERR_ARG;
+  if (A->n_rows != n_constraints || B->n_rows != n_constraints || C->n_rows != n_constraints) return OZL_ERR_ARG;
+  if (n_instance == 0 || n_instance > n_vars) return OZL_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const uint64_t need = (uint64_t)n_constraints + n_instance;   // ark: domain over num_constraints + num_inputs
+  uint32_t log_n = 0;
+  while (((uint64_t)1 << log_n) < need) log_n++;
+  const int two_adicity = pairing == OZL_PAIRING_BN254 ? 28 : 32;
+  if ((int)log_n > two_adicity || log_n > 30) return OZL_ERR_DOMAIN;
+  const size_t n = (size_t)1 << log_n;
+  // handle sanity
+  Bases *ba, *bb1, *bb2, *bh, *bl;
+  for (auto hp : {std::make_pair(a_query, &ba), std::make_pair(b_g1_query, &bb1), std::make_pair(b_g2_query, &bb2),
+                  std::make_pair(h_query, &bh), std::make_pair(l_query, &bl)}) {
+    auto it = ctx->bases.find(hp.first);
+    if (it == ctx->bases.end()) return OZL_ERR_HANDLE;
+    *hp.second = &it->second;
+  }
+  if (ba->curve != g1_curve(pairing) || bb1->curve != g1_curve(pairing) || bh->curve != g1_curve(pairing) ||
+      bl->curve != g1_curve(pairing) || bb2->curve != g2_curve(pairing)) return OZL_ERR_ARG;
+  if (ba->n < n_vars || bb1->n < n_vars || bb2->n < n_vars || bh->n < n - 1 || bl->n < n_vars - n_instance) return OZL_ERR_ARG;
+  Groth16Pk* pkp = new (std::nothrow) Groth16Pk();
+  if (!pkp) return OZL_ERR_OOM;
+  pkp->pairing = pairing;
+  pkp->n_constraints = n_constraints; pkp->n_instance = n_instance; pkp->n_vars = n_vars;
+  pkp->log_n = log_n;
+  const int rc = pk_build(ctx, pkp, A, B, C, coef_table, n_coef, alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2);
+  if (rc) {
+    destroy_pk(ctx, pkp);   // the five bases handles are not the pk's yet: the caller keeps them
+    return rc;
+  }
+  pkp->h_a = a_query; pkp->h_b1 = b_g1_query; pkp->h_b2 = b_g2_query; pkp->h_h = h_query; pkp->h_l = l_query;
+  ctx->pk_deleter = destroy_pk;
+  *pk_handle = ctx->next_pk++;
+  ctx->pks[*pk_handle] = pkp;
   return OZL_OK;
 }
 
 int ozl_groth16_pk_destroy(ozl_ctx* ctx, uint32_t pk_handle) {
   if (!ctx) return OZL_ERR_ARG;
-  auto it = pk_registry().find(pk_handle);
-  if (it == pk_registry().end()) return OZL_ERR_HANDLE;
-  destroy_pk(ctx, it->second);
-  pk_registry().erase(it);
+  auto it = ctx->pks.find(pk_handle);
+  if (it == ctx->pks.end()) return OZL_ERR_HANDLE;
+  Groth16Pk* pkp = it->second;
+  ctx->pks.erase(it);
+  destroy_pk(ctx, pkp);
   return OZL_OK;
 }
 
 int ozl_groth16_domain_size(ozl_ctx* ctx, uint32_t pk_handle, uint32_t* out) {
   if (!ctx || !out) return OZL_ERR_ARG;
-  auto it = pk_registry().find(pk_handle);
-  if (it == pk_registry().end()) return OZL_ERR_HANDLE;
-  *out = 1u << it->second.log_n;
+  Groth16Pk* pkp = find_pk(ctx, pk_handle);
+  if (!pkp) return OZL_ERR_HANDLE;
+  *out = 1u << pkp->log_n;
   return OZL_OK;
 }
 
 int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const uint64_t* r_scalar, const uint64_t* s_scalar,
                       uint64_t* proof_a, uint64_t* proof_b, uint64_t* proof_c, uint64_t* h_out) {
   if (!ctx || !z || !r_scalar || !s_scalar || !proof_a || !proof_b || !proof_c) return OZL_ERR_ARG;
-  auto it = pk_registry().find(pk_handle);
-  if (it == pk_registry().end()) return OZL_ERR_HANDLE;
-  Groth16Pk& pk = it->second;
+  Groth16Pk* pkp = find_pk(ctx, pk_handle);
+  if (!pkp) return OZL_ERR_HANDLE;      // unknown, destroyed, or created on another context
+  Groth16Pk& pk = *pkp;
+  const Bases *q_a, *q_b1, *q_b2, *q_h, *q_l;
+  for (auto hp : {std::make_pair(pk.h_a, &q_a), std::make_pair(pk.h_b1, &q_b1), std::make_pair(pk.h_b2, &q_b2),
+                  std::make_pair(pk.h_h, &q_h), std::make_pair(pk.h_l, &q_l)}) {
+    auto it = ctx->bases.find(hp.first);
+    if (it == ctx->bases.end()) return OZL_ERR_HANDLE;
+    *hp.second = &it->second;
+  }
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const OzlFieldOps* f = field_ops(fr_field(pk.pairing));
   const OzlCurveOps* o1 = g1_ops(pk.pairing);
@@ -309,7 +382,6 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     return cudaMemcpyAsync(dst, src, words * 4, cudaMemcpyDeviceToDevice, q);
   };
   {
-    auto& reg = ctx->bases;
     CUDA_TRY(ctx, cudaMemcpyAsync(S + 16, one, 32, cudaMemcpyHostToDevice, pk.s2));
     f->mul_canonical(pk.s2, S + 0, S + 8, S + 24);
     CUDA_TRY(ctx, cp_on(pk.s2, fs + 0, S + 8, 8));
@@ -318,13 +390,13 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     CUDA_TRY(ctx, cp_on(pk.s2, fs + 24, S + 0, 8));
     o1->scalar_mul_table(pk.s2, pk.tables_g1, fs, 4, fixed_out);
     o2->scalar_mul_table(pk.s2, pk.tables_g2, S + 8, 1, g2_fixed_out);
-    if ((rc = ozl_rt_msm(ctx, pk.ws2, pk.s2, reg[pk.h_b2], pk.zc, m, acc_g2))) return rc;
-    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, reg[pk.h_a], pk.zc, m, acc + 2 * J1))) return rc;
-    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, reg[pk.h_b1], pk.zc, m, acc + 3 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, pk.ws2, pk.s2, *q_b2, pk.zc, m, acc_g2))) return rc;
+    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, *q_a, pk.zc, m, acc + 2 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, *q_b1, pk.zc, m, acc + 3 * J1))) return rc;
     CUDA_TRY(ctx, cp_on(pk.s1, vs + 0, pk.rs + 8, 8));
     CUDA_TRY(ctx, cp_on(pk.s1, vs + 8, pk.rs + 0, 8));
     o1->scalar_mul_var(pk.s1, acc + 2 * J1, vs, 2, var_out);   // acc[2] = a_acc, acc[3] = b1_acc (adjacent)
-    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, reg[pk.h_l], pk.zc + (size_t)ni * 8, m - ni, acc + 1 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, *q_l, pk.zc + (size_t)ni * 8, m - ni, acc + 1 * J1))) return rc;
     CUDA_TRY(ctx, cudaEventRecord(pk.ev_s1, pk.s1));
     CUDA_TRY(ctx, cudaEventRecord(pk.ev_s2, pk.s2));
   }
@@ -347,8 +419,7 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
 
   {
     // MSM outputs (Jacobian): acc[0]=h, [1]=l, [2]=a, [3]=b1 in G1 slots; b2 in a G2 slot after them
-    auto& reg = ctx->bases;
-    if ((rc = ozl_rt_msm(ctx, ctx->ws, st, reg[pk.h_h], pk.hc, n - 1, acc + 0 * J1))) return rc;
+    if ((rc = ozl_rt_msm(ctx, ctx->ws, st, *q_h, pk.hc, n - 1, acc + 0 * J1))) return rc;
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, pk.ev_s1, 0));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, pk.ev_s2, 0));
 

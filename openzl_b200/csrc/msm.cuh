@@ -40,10 +40,16 @@ struct MsmPlan {
 // Digit extraction + histogram.  Writes the signed digit of every (window, scalar) pair to the
 // window-major array digits[w * n + i] (encoded bucket+1, sign in bit 31, 0 = no contribution) so
 // that the scatter can run window by window over contiguous 4-byte entries.
-static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t n,
-                               int c, int W, int Wc, uint32_t B, uint32_t* __restrict__ counts, uint32_t* __restrict__ digits) {
+// `first` is the index of the batch's first scalar within the MSM (inf_mask is indexed globally); n is
+// the batch length.  err_flags: bit 0 is raised when a scalar does not fit the window plan, i.e. it has
+// bits at or above W*c or the signed recoding carries out of the top window -- impossible for canonical
+// scalars (< r < 2^scalar_bits), so it flags non-canonical input instead of returning a wrong point.
+static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf_mask, uint32_t first, uint32_t n,
+                               int c, int W, int Wc, uint32_t B, uint32_t* __restrict__ counts, uint32_t* __restrict__ digits,
+                               uint32_t* __restrict__ err_flags) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const bool skip = inf_mask && ((inf_mask[i >> 3] >> (i & 7)) & 1);
+    const uint32_t gi = first + i;
+    const bool skip = inf_mask && ((inf_mask[gi >> 3] >> (gi & 7)) & 1);
     uint32_t s[8];
     const uint4* sp = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
     uint4 a = sp[0], b = sp[1];
@@ -74,6 +80,14 @@ static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8
       if (v && (uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u))
         atomicAdd(&counts[(uint32_t)(w % Wc) * B + (v - 1)], (uint32_t)__popc(peers));
     }
+    // bits the plan does not cover
+    const int top = W * c;
+    uint32_t left = carry;
+    if (top < 256) {
+      left |= s[top >> 5] >> (top & 31);
+      for (int l = (top >> 5) + 1; l < 8; l++) left |= s[l];
+    }
+    if (left && !skip) atomicOr(err_flags, 1u);
   }
 }
 
@@ -440,38 +454,71 @@ k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ o
   }
 }
 
-// Sum of each ordinary bucket's slice partials, one thread per bucket, into the bucket's first slot
-// (heavy buckets were already folded there by k_collapse_heavy).  Taking these additions out of
-// k_bucket_reduce shortens its dependent chain -- a lone thread pays ~15 us per 381-bit addition, so
-// the reduce stage of a small MSM is bound by chain length, not by work.
+// Sum of each bucket's slice partials, one thread per bucket, into the bucket's first slot of region 0,
+// g + offsets0[g] / L0 (a slot no other bucket uses, even when the bucket is empty in region 0: slots
+// g + t are strictly increasing along (bucket, slice) runs).  Heavy buckets were already folded into
+// their first slot by k_collapse_heavy.  A plain MSM has one region; an MSM whose scalars arrive in
+// point-range batches (runtime.cuh: msm_run_batched) has one region per batch, each with its own
+// offsets and slice length.  Taking these additions out of k_bucket_reduce shortens its dependent chain
+// -- a lone thread pays microseconds per addition, so the reduce stage of a small MSM is bound by chain
+// length, not by work.
+struct FoldRegions {
+  int J;
+  uint32_t* partials[8];
+  const uint32_t* offsets[8];
+  uint32_t L[8];
+  uint32_t heavy_t[8];
+};
+
 template <class F>
 __global__ void __launch_bounds__(128)
-k_bucket_fold(uint32_t* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t NB, uint32_t L, uint32_t heavy_t) {
+k_bucket_fold(FoldRegions R, uint32_t NB) {
   constexpr int XY = 4 * F::N;
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= NB) return;
-  const uint32_t o0 = offsets[g], o1 = offsets[g + 1];
-  if (o1 <= o0) return;
-  const uint32_t t0 = o0 / L, t1 = (o1 - 1) / L;
-  if (t1 == t0 || t1 - t0 + 1 > heavy_t) return;
-  XYZZ<F> acc = XYZZ<F>::load(partials + (size_t)(g + t0) * XY);
-  for (uint32_t t = t0 + 1; t <= t1; t++) {
-    XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + t) * XY);
-    acc.add(p);
+  if (R.J == 1) {
+    const uint32_t L = R.L[0];
+    uint32_t* partials = R.partials[0];
+    const uint32_t o0 = R.offsets[0][g], o1 = R.offsets[0][g + 1];
+    if (o1 <= o0) return;
+    const uint32_t t0 = o0 / L, t1 = (o1 - 1) / L;
+    if (t1 == t0 || t1 - t0 + 1 > R.heavy_t[0]) return;
+    XYZZ<F> acc = XYZZ<F>::load(partials + (size_t)(g + t0) * XY);
+    for (uint32_t t = t0 + 1; t <= t1; t++) {
+      XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + t) * XY);
+      acc.add(p);
+    }
+    acc.store(partials + (size_t)(g + t0) * XY);
+    return;
   }
-  acc.store(partials + (size_t)(g + t0) * XY);
+  XYZZ<F> acc = XYZZ<F>::identity();
+  for (int j = 0; j < R.J; j++) {
+    const uint32_t L = R.L[j];
+    const uint32_t* partials = R.partials[j];
+    const uint32_t o0 = R.offsets[j][g], o1 = R.offsets[j][g + 1];
+    if (o1 <= o0) continue;
+    const uint32_t t0 = o0 / L;
+    uint32_t t1 = (o1 - 1) / L;
+    if (t1 - t0 + 1 > R.heavy_t[j]) t1 = t0;      // collapsed: the total already sits in the first slot
+    for (uint32_t t = t0; t <= t1; t++) {
+      XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + t) * XY);
+      acc.add(p);
+    }
+  }
+  acc.store(R.partials[0] + (size_t)(g + R.offsets[0][g] / R.L[0]) * XY);
 }
 
 // ---------------------------------------------------------------------------------------------
 // bucket reduction: for a chunk of buckets [lo, lo + chunk) of window w computes
 //   sum_b (b + 1) * B_b   =   sum_b (b - lo + 1) B_b  +  lo * sum_b B_b
 // by the running-sum recurrence (2 additions per bucket) plus one small scalar multiple.
-// B_b itself is the sum of the bucket's slice partials (see k_accumulate).
+// B_b sits in the bucket's first slot (k_bucket_fold).  dense = 1: every bucket's slot was written by
+// the fold (batched MSM; the identity for an empty bucket), so occupancy is not read from the offsets.
 // ---------------------------------------------------------------------------------------------
 template <class F>
 __global__ void __launch_bounds__(128)
 k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t L, uint32_t total_chunks,
-                uint32_t K, uint32_t B, uint32_t chunk, uint32_t* __restrict__ chunk_out) {
+                uint32_t K, uint32_t B, uint32_t chunk, int dense, uint32_t* __restrict__ chunk_out) {
   constexpr int XY = 4 * F::N;
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total_chunks) return;
@@ -482,8 +529,7 @@ k_bucket_reduce(const uint32_t* __restrict__ partials, const uint32_t* __restric
   for (uint32_t j = chunk; j-- > 0;) {
     const uint32_t g = w * B + lo + j;
     const uint32_t o0 = offsets[g], o1 = offsets[g + 1];
-    if (o1 > o0) {
-      // the bucket's total sits in its first slot (k_bucket_fold / k_collapse_heavy)
+    if (dense || o1 > o0) {
       XYZZ<F> p = XYZZ<F>::load(partials + (size_t)(g + o0 / L) * XY);
       running.add(p);
     }

@@ -18,8 +18,12 @@ void vanishing_inv_entry(cudaStream_t st, int log_n, uint32_t* out) {
 void mul_canonical_entry(cudaStream_t st, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   ozl::k_mul_canonical<P_><<<1, 32, 0, st>>>(a, b, out);
 }
+void poseidon_entry(cudaStream_t st, uint32_t* states, uint32_t batch, int width, int full_rounds, int partial_rounds,
+                    const uint32_t* round_keys, const uint32_t* mds) {
+  if (batch) ozl::k_poseidon_permute<P_><<<(batch + 127) / 128, 128, 0, st>>>(states, batch, width, full_rounds, partial_rounds, round_keys, mds);
+}
 }  // namespace
 int ozl_ntt_run_bls12_381_fr(cudaStream_t st, ozl::NttWorkspace& ws, uint32_t* d, uint32_t log_n, bool inverse, bool coset, int* launches) {
   return ozl::ntt_run<P_>(st, ws, OZL_BLS12_381_FR, d, log_n, inverse, coset, launches);
 }
-const OzlFieldOps ozl_fops_bls12_381_fr = {ozl_ntt_run_bls12_381_fr, spmv_entry, from_mont_entry, h_pointwise_entry, vanishing_inv_entry, mul_canonical_entry};
+const OzlFieldOps ozl_fops_bls12_381_fr = {ozl_ntt_run_bls12_381_fr, spmv_entry, from_mont_entry, h_pointwise_entry, vanishing_inv_entry, mul_canonical_entry, poseidon_entry};

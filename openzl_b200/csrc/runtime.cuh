@@ -40,11 +40,14 @@ struct Bases {
 // Scratch buffers of one MSM in flight.  The context owns one; the Groth16 prover owns two more so
 // that independent MSMs can run on separate streams and overlap their latency-bound tails.
 struct MsmWorkspace {
-  DevBuf counts, offsets, tile_sums, sorted, digits, partials, chunk_out, window_out, misc;
+  DevBuf counts, tile_sums, sorted, digits, chunk_out, window_out, misc;
+  DevBuf offsets[8], partials[8];     // per point-range batch (MSM_MAX_BATCHES); [0] alone for a plain MSM
   // batched-affine pair levels (msm_batch.cuh): per-level offsets, chunk table, ping-pong point
   // buffers, prefix-product scratch, and the last level's point lists
   DevBuf lvl_off, pair_tab, pair_a, pair_b, pair_pre, lvl_pts;
 };
+
+struct Groth16Pk;   // groth16.cu
 
 struct Stage {
   std::string name;
@@ -78,7 +81,13 @@ struct ozl_ctx {
   DevBuf pipe_scalars[2], pipe_out[2];
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   unsigned pipe_idx = 0;
+  cudaEvent_t ev_batch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // batch arrivals of a host-scalar MSM
+  cudaEvent_t ev_prior = nullptr;   // "everything enqueued so far on the MSM's stream" (the staging buffer's last readers)
   NttWorkspace ntt_ws;
+  // Groth16 proving keys resident on this context's device (groth16.cu); owned by the context
+  std::map<uint32_t, ozl_rt::Groth16Pk*> pks;
+  uint32_t next_pk = 1;
+  void (*pk_deleter)(ozl_ctx*, ozl_rt::Groth16Pk*) = nullptr;
 };
 
 namespace ozl_rt {
@@ -168,6 +177,15 @@ inline int coord_u32(int curve) {
 }
 inline int scalar_bits(int curve) { return (curve == OZL_BLS12_381_G1 || curve == OZL_BLS12_381_G2) ? 255 : 254; }
 
+inline uint32_t slice_len(uint64_t entries) {
+  uint64_t L = entries / ((uint64_t)148 * 384);
+  if (L > 128) L = 128;
+  if (L < 8) L = 8;
+  static const int kForceL = []() { const char* e = getenv("OZL_MSM_L"); return e ? atoi(e) : 0; }();
+  if (kForceL >= 8) L = (uint64_t)kForceL;
+  return (uint32_t)L & ~7u;   // multiple of 8 entries: slices start 32-byte aligned (TMA needs 16)
+}
+
 // Window width: minimise field multiplications  n*W*10 (mixed adds) + 2*Wc*B*95 + (n*W/128)*45
 // (bucket reduction: two adds per bucket and one per slice partial, weighted by the efficiency
 // measured for the reduce kernels on B200: c=20 beats c=22 at 2^26, c=16 beats c=13 at 2^20), where Wc = ceil(W / factor) bucket sets remain after base precomputation.
@@ -196,16 +214,7 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0, in
   p.B = 1u << (p.c - 1);
   p.Wc = fixed_Wc ? fixed_Wc : p.W;
   p.NB = (uint32_t)p.Wc * p.B;
-  // slice length: 128 entries per thread when there is enough work to fill the chip, shorter otherwise
-  {
-    const uint64_t E = (uint64_t)n * p.W;
-    uint64_t L = E / ((uint64_t)148 * 384);
-    if (L > 128) L = 128;
-    if (L < 8) L = 8;
-    static const int kForceL = []() { const char* e = getenv("OZL_MSM_L"); return e ? atoi(e) : 0; }();
-    if (kForceL >= 8) L = (uint64_t)kForceL;
-    p.L = (uint32_t)L & ~7u;   // multiple of 8 entries: slices start 32-byte aligned (TMA needs 16)
-  }
+  p.L = slice_len((uint64_t)n * p.W);   // 128 entries per accumulate thread when there is enough work to fill the chip, shorter otherwise
   uint32_t chunk = p.B / 4096;
   if (chunk < 4) chunk = 4;
   if (chunk > 16) chunk = 16;
@@ -326,131 +335,176 @@ int run_pair_levels(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
   return OZL_OK;
 }
 
+// One MSM = J >= 1 point-range BATCHES that share the bucket sets.  Every batch is digit-extracted,
+// sorted and accumulated on its own (into its own region of slice partials); the bucket fold then sums a
+// bucket's partials over all regions and the reduction runs once.  J = 1 is the plain pipeline.  J > 1
+// exists for host scalars: batch j is accumulated while batch j+1 is still crossing PCIe, so the
+// host->device copy of an `ozl_msm` call hides under the accumulation instead of preceding it
+// (the copy is issued HERE, batch by batch, so that it also overlaps when the caller's memory is
+// pageable and cudaMemcpyAsync blocks the host thread).
+static constexpr int MSM_MAX_BATCHES = 8;
+
+struct MsmBatches {
+  int J = 1;
+  size_t first[MSM_MAX_BATCHES] = {0};
+  size_t count[MSM_MAX_BATCHES] = {0};
+  // host source (optional): batch j is copied to d_scalars + first[j] on copy_stream, then awaited by the MSM's stream
+  const uint64_t* h_scalars = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t* ev = nullptr;            // J events
+};
+
 template <class F>
-int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, const uint32_t* d_scalars, size_t n,
-            uint32_t* d_out) {
+int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, const uint32_t* d_scalars, size_t n,
+                    const MsmBatches& mb, uint32_t* d_out) {
   constexpr int XY = 4 * F::N;
   const MsmPlan p = b.factor > 1 ? make_plan(b.curve, n, b.pc, b.pWc) : make_plan(b.curve, n, ctx->forced_c);
   if ((uint64_t)n * p.W >= 0xffffffffull || (uint64_t)b.n * b.factor >= 0x7fffffffull) {
-    ctx->last_error = "msm: n too large for 32-bit indices";
+    ctx->last_error = "msm: n * windows must stay below 2^32 and n * copies below 2^31 (32-bit sort entries)";
     return OZL_ERR_ARG;
   }
-  int r;
-  if ((r = ensure(ctx, ws.counts, (size_t)p.NB * 4))) return r;
-  if ((r = ensure(ctx, ws.offsets, ((size_t)p.NB + 1) * 4))) return r;
-  if ((r = ensure(ctx, ws.sorted, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
-  if ((r = ensure(ctx, ws.digits, std::max<size_t>((size_t)n * p.W, 1) * 4))) return r;
-  if ((r = ensure(ctx, ws.partials, (size_t)p.max_slots * XY * 4))) return r;
-  if ((r = ensure(ctx, ws.chunk_out, ((size_t)p.Wc * p.K + (size_t)p.Wc * 64) * XY * 4))) return r;
-  if ((r = ensure(ctx, ws.window_out, (size_t)p.Wc * XY * 4))) return r;
-  if ((r = ensure(ctx, ws.misc, 64))) return r;
-
-  uint32_t* counts = (uint32_t*)ws.counts.p;
-  uint32_t* offsets = (uint32_t*)ws.offsets.p;
-  uint32_t* sorted = (uint32_t*)ws.sorted.p;
-  uint32_t* digits = (uint32_t*)ws.digits.p;
-  uint32_t* partials = (uint32_t*)ws.partials.p;
-  uint32_t* chunk_out = (uint32_t*)ws.chunk_out.p;
-  uint32_t* window_out = (uint32_t*)ws.window_out.p;
-  uint32_t* work_counter = (uint32_t*)ws.misc.p;
-  const int grid_io = ctx->sm_count * 8;
-
-  STAGE_ON(ctx, "digits_count", st);
-  CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)p.NB * 4, st));
-  CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 64, st));
-  k_count<<<grid_io, 256, 0, st>>>(d_scalars, b.d_inf, (uint32_t)n, p.c, p.W, p.Wc, p.B, counts, digits);
-  LAUNCH_CHECK(ctx);
-  STAGE_END(ctx);
-
-  // Batched-affine pair levels (msm_batch.cuh): T halving levels before the XYZZ accumulation.
+  // Batched-affine pair levels (msm_batch.cuh): T halving levels before the XYZZ accumulation (single batch only).
   BatchConfig bc = batch_config();
   if (ctx->batch_levels >= 0) {      // explicit request: honoured at every size
     bc.levels = ctx->batch_levels;
     bc.min_entries = 0;
   }
-  const int T = (n && (uint64_t)n * p.W >= bc.min_entries) ? bc.levels : 0;
+  const int T = (mb.J == 1 && n && (uint64_t)n * p.W >= bc.min_entries) ? bc.levels : 0;
+  const int J = mb.J;
+  size_t max_nj = 0;
+  uint32_t Lj[MSM_MAX_BATCHES], heavy[MSM_MAX_BATCHES];
+  for (int j = 0; j < J; j++) {
+    max_nj = std::max(max_nj, mb.count[j]);
+    Lj[j] = J == 1 ? p.L : slice_len((uint64_t)mb.count[j] * p.W);
+  }
+  int r;
+  if ((r = ensure(ctx, ws.counts, (size_t)p.NB * 4))) return r;
+  if ((r = ensure(ctx, ws.sorted, std::max<size_t>(max_nj * p.W, 1) * 4))) return r;
+  if ((r = ensure(ctx, ws.digits, std::max<size_t>(max_nj * p.W, 1) * 4))) return r;
+  for (int j = 0; j < J; j++) {
+    const size_t slots = (size_t)p.NB + ((size_t)mb.count[j] * p.W) / Lj[j] + 2;
+    if ((r = ensure(ctx, ws.offsets[j], ((size_t)p.NB + 1) * 4))) return r;
+    if ((r = ensure(ctx, ws.partials[j], slots * XY * 4))) return r;
+  }
+  if ((r = ensure(ctx, ws.chunk_out, ((size_t)p.Wc * p.K + (size_t)p.Wc * 64) * XY * 4))) return r;
+  if ((r = ensure(ctx, ws.window_out, (size_t)p.Wc * XY * 4))) return r;
+  if ((r = ensure(ctx, ws.misc, 64))) return r;
   uint32_t* lvl_off = nullptr;
   if (T) {
     if ((r = ensure(ctx, ws.lvl_off, (size_t)T * ((size_t)p.NB + 1) * 4))) return r;
     lvl_off = (uint32_t*)ws.lvl_off.p;
   }
 
-  STAGE_ON(ctx, "scan", st);
-  if ((r = run_scan(ctx, ws, st, counts, p.NB, offsets, ScanIdentity{1}))) return r;
-  // level-l lists hold ceil(count / 2^l) entries per bucket (counts are consumed by the scatter below)
-  for (int l = 1; l <= T; l++)
-    if ((r = run_scan(ctx, ws, st, counts, p.NB, lvl_off + (size_t)(l - 1) * (p.NB + 1), ScanCeilDiv{1u << l}))) return r;
-  STAGE_END(ctx);
+  uint32_t* counts = (uint32_t*)ws.counts.p;
+  uint32_t* sorted = (uint32_t*)ws.sorted.p;
+  uint32_t* digits = (uint32_t*)ws.digits.p;
+  uint32_t* chunk_out = (uint32_t*)ws.chunk_out.p;
+  uint32_t* window_out = (uint32_t*)ws.window_out.p;
+  uint32_t* work_counter = (uint32_t*)ws.misc.p;     // [0] slice counter of the accumulation, [8] input-error flags
+  const int grid_io = ctx->sm_count * 8;
+  FoldRegions regions;
+  regions.J = J;
+  CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 64, st));
 
-  STAGE_ON(ctx, "scatter", st);
-  {
-    // bucket ranges of 2^18 buckets per pass (8 MB of open sectors), range-major so a bucket's region
-    // is completed while its sectors are still in L2.  Measured at 2^26, c = 22 (2^21 buckets):
-    // 34.2 / 27.9 / 26.9 / 23.3 ms with 1 / 2 / 4 / 8 ranges, re-reading the digits included.
-    static const int kForceParts = []() { const char* e = getenv("OZL_MSM_SCATTER_PARTS"); return e ? atoi(e) : 0; }();
-    uint32_t parts = kForceParts > 0 ? (uint32_t)kForceParts : std::min<uint32_t>(16u, std::max<uint32_t>(1u, p.B >> 18));
-    if (parts > p.B) parts = p.B;
-    const uint32_t span = (p.B + parts - 1) / parts;
-    for (uint32_t q = 0; q < parts && n; q++) {
-      const uint32_t lo = q * span, hi = std::min<uint32_t>(p.B, lo + span);
-      for (int w = 0; w < p.W; w++) {
-        k_scatter_window<<<grid_io, 256, 0, st>>>(digits + (size_t)w * n, (uint32_t)n, (uint32_t)(w % p.Wc) * p.B,
-                                                 (uint32_t)((size_t)(w / p.Wc) * b.n), offsets, counts, sorted, lo, hi);
-        LAUNCH_CHECK(ctx);
+  for (int j = 0; j < J; j++) {
+    const size_t first = mb.first[j], nj = mb.count[j];
+    uint32_t* offsets = (uint32_t*)ws.offsets[j].p;
+    uint32_t* partials = (uint32_t*)ws.partials[j].p;
+    const uint32_t* sc = d_scalars + first * 8;
+    if (mb.h_scalars) {
+      if (nj) CUDA_TRY(ctx, cudaMemcpyAsync((void*)sc, mb.h_scalars + first * 4, nj * 32, cudaMemcpyHostToDevice, mb.copy_stream));
+      CUDA_TRY(ctx, cudaEventRecord(mb.ev[j], mb.copy_stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(st, mb.ev[j], 0));
+    }
+
+    STAGE_ON(ctx, "digits_count", st);
+    CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)p.NB * 4, st));
+    if (j) CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 4, st));
+    k_count<<<grid_io, 256, 0, st>>>(sc, b.d_inf, (uint32_t)first, (uint32_t)nj, p.c, p.W, p.Wc, p.B, counts, digits, work_counter + 8);
+    LAUNCH_CHECK(ctx);
+    STAGE_END(ctx);
+
+    STAGE_ON(ctx, "scan", st);
+    if ((r = run_scan(ctx, ws, st, counts, p.NB, offsets, ScanIdentity{1}))) return r;
+    // level-l lists hold ceil(count / 2^l) entries per bucket (counts are consumed by the scatter below)
+    for (int l = 1; l <= T; l++)
+      if ((r = run_scan(ctx, ws, st, counts, p.NB, lvl_off + (size_t)(l - 1) * (p.NB + 1), ScanCeilDiv{1u << l}))) return r;
+    STAGE_END(ctx);
+
+    STAGE_ON(ctx, "scatter", st);
+    {
+      // bucket ranges of 2^18 buckets per pass (8 MB of open sectors), range-major so a bucket's region
+      // is completed while its sectors are still in L2.  Measured at 2^26, c = 22 (2^21 buckets):
+      // 34.2 / 27.9 / 26.9 / 23.3 ms with 1 / 2 / 4 / 8 ranges, re-reading the digits included.
+      static const int kForceParts = []() { const char* e = getenv("OZL_MSM_SCATTER_PARTS"); return e ? atoi(e) : 0; }();
+      uint32_t parts = kForceParts > 0 ? (uint32_t)kForceParts : std::min<uint32_t>(16u, std::max<uint32_t>(1u, p.B >> 18));
+      if (parts > p.B) parts = p.B;
+      const uint32_t span = (p.B + parts - 1) / parts;
+      for (uint32_t q = 0; q < parts && nj; q++) {
+        const uint32_t lo = q * span, hi = std::min<uint32_t>(p.B, lo + span);
+        for (int w = 0; w < p.W; w++) {
+          k_scatter_window<<<grid_io, 256, 0, st>>>(digits + (size_t)w * nj, (uint32_t)nj, (uint32_t)(w % p.Wc) * p.B,
+                                                   (uint32_t)((size_t)(w / p.Wc) * b.n + first), offsets, counts, sorted, lo, hi);
+          LAUNCH_CHECK(ctx);
+        }
       }
     }
-  }
-  STAGE_END(ctx);
-
-  const uint32_t* acc_offsets = offsets;   // offsets of the lists the XYZZ accumulation walks
-  uint32_t acc_L = p.L;
-  if (T) {
-    STAGE_ON(ctx, "pair_levels", st);
-    if ((r = run_pair_levels<F>(ctx, ws, st, b, p, bc, T, n, sorted, offsets, lvl_off))) return r;
     STAGE_END(ctx);
-    acc_offsets = lvl_off + (size_t)(T - 1) * (p.NB + 1);
-    uint64_t L = (((uint64_t)n * p.W) >> T) / ((uint64_t)148 * 384);
-    if (L > 128) L = 128;
-    if (L < 8) L = 8;
-    acc_L = (uint32_t)L & ~7u;
-    const size_t slots = (size_t)p.NB + ((((size_t)n * p.W) >> T) + p.NB) / acc_L + 2;
-    if ((r = ensure(ctx, ws.partials, slots * XY * 4))) return r;
-    partials = (uint32_t*)ws.partials.p;
-  }
 
-  STAGE_ON(ctx, "accumulate", st);
-  if (T) {
-    k_accumulate<F, true><<<ctx->sm_count * 4, 128, 0, st>>>((const uint32_t*)ws.lvl_pts.p, nullptr, acc_offsets, p.NB, acc_L, work_counter, partials);
-  } else {
-    // TMA-staged index stream by default; OZL_ACC_TMA=0 selects the plain global-load variant
-    static const bool use_tma = []() { const char* e = getenv("OZL_ACC_TMA"); return !(e && e[0] == '0'); }();
-    if (use_tma) k_accumulate_tma<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, p.L, work_counter, partials);
-    else k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, p.L, work_counter, partials);
+    const uint32_t* acc_offsets = offsets;   // offsets of the lists the XYZZ accumulation walks
+    uint32_t acc_L = Lj[j];
+    if (T) {
+      STAGE_ON(ctx, "pair_levels", st);
+      if ((r = run_pair_levels<F>(ctx, ws, st, b, p, bc, T, nj, sorted, offsets, lvl_off))) return r;
+      STAGE_END(ctx);
+      acc_offsets = lvl_off + (size_t)(T - 1) * (p.NB + 1);
+      acc_L = slice_len(((uint64_t)nj * p.W) >> T);
+      const size_t slots = (size_t)p.NB + ((((size_t)nj * p.W) >> T) + p.NB) / acc_L + 2;
+      if ((r = ensure(ctx, ws.partials[j], slots * XY * 4))) return r;
+      partials = (uint32_t*)ws.partials[j].p;
+    }
+
+    STAGE_ON(ctx, "accumulate", st);
+    if (T) {
+      k_accumulate<F, true><<<ctx->sm_count * 4, 128, 0, st>>>((const uint32_t*)ws.lvl_pts.p, nullptr, acc_offsets, p.NB, acc_L, work_counter, partials);
+    } else {
+      // TMA-staged index stream by default; OZL_ACC_TMA=0 selects the plain global-load variant
+      static const bool use_tma = []() { const char* e = getenv("OZL_ACC_TMA"); return !(e && e[0] == '0'); }();
+      if (use_tma) k_accumulate_tma<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+    }
+    LAUNCH_CHECK(ctx);
+    STAGE_END(ctx);
+
+    // "heavy" = far more slice partials than the average bucket has (skew), not merely many
+    const uint32_t acc_entries = (uint32_t)std::min<uint64_t>(T ? ((((uint64_t)nj * p.W) >> T) + p.NB) : (uint64_t)nj * p.W, 0xffffffffull);
+    heavy[j] = std::max<uint32_t>(HEAVY_T_MIN, 4u * (acc_entries / acc_L / p.NB + 2u));
+    regions.partials[j] = partials;
+    regions.offsets[j] = acc_offsets;
+    regions.L[j] = acc_L;
+    regions.heavy_t[j] = heavy[j];
   }
-  LAUNCH_CHECK(ctx);
-  STAGE_END(ctx);
 
   STAGE_ON(ctx, "bucket_reduce", st);
-  // "heavy" = far more slice partials than the average bucket has (skew), not merely many
-  const uint32_t acc_entries = (uint32_t)std::min<uint64_t>(T ? ((((uint64_t)n * p.W) >> T) + p.NB) : (uint64_t)n * p.W, 0xffffffffull);
-  const uint32_t heavy_t = std::max<uint32_t>(HEAVY_T_MIN, 4u * (acc_entries / acc_L / p.NB + 2u));
   if (n) {
     // heavy-bucket collapse: 3 passes cover 2^30 partials per bucket; no-ops when nothing is heavy
     const dim3 hgrid((unsigned)std::min<uint32_t>((p.NB + 31) / 32, (uint32_t)ctx->sm_count * 16), HEAVY_GY);
-    uint32_t stride = 1;
-    for (int pass = 0; pass < 3; pass++) {
-      if ((uint64_t)n * p.W / acc_L + 1 < stride) break;
-      k_collapse_heavy<F><<<hgrid, 32, 0, st>>>(partials, acc_offsets, p.NB, acc_L, stride, heavy_t);
-      LAUNCH_CHECK(ctx);
-      stride *= HEAVY_GROUP;
+    for (int j = 0; j < J; j++) {
+      if (!mb.count[j] && J > 1) continue;
+      uint32_t stride = 1;
+      for (int pass = 0; pass < 3; pass++) {
+        if ((uint64_t)mb.count[j] * p.W / regions.L[j] + 1 < stride) break;
+        k_collapse_heavy<F><<<hgrid, 32, 0, st>>>(regions.partials[j], regions.offsets[j], p.NB, regions.L[j], stride, heavy[j]);
+        LAUNCH_CHECK(ctx);
+        stride *= HEAVY_GROUP;
+      }
     }
-  }
-  if (n) {
-    k_bucket_fold<F><<<(p.NB + 127) / 128, 128, 0, st>>>(partials, acc_offsets, p.NB, acc_L, heavy_t);
+    k_bucket_fold<F><<<(p.NB + 127) / 128, 128, 0, st>>>(regions, p.NB);
     LAUNCH_CHECK(ctx);
   }
   const uint32_t total_chunks = (uint32_t)p.Wc * p.K;
-  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(partials, acc_offsets, acc_L, total_chunks, p.K, p.B, p.chunk, chunk_out);
+  k_bucket_reduce<F><<<(total_chunks + 127) / 128, 128, 0, st>>>(regions.partials[0], regions.offsets[0], regions.L[0], total_chunks, p.K, p.B, p.chunk,
+                                                                  (J > 1 && n) ? 1 : 0, chunk_out);
   LAUNCH_CHECK(ctx);
   {
     const uint32_t Y = p.K >= 4096 ? 64 : 1;          // fan-out of the first summation launch
@@ -473,6 +527,16 @@ int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, con
   return OZL_OK;
 }
 
+template <class F>
+int msm_run(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases& b, const uint32_t* d_scalars, size_t n,
+            uint32_t* d_out) {
+  MsmBatches mb;
+  mb.J = 1;
+  mb.first[0] = 0;
+  mb.count[0] = n;
+  return msm_run_batched<F>(ctx, ws, st, b, d_scalars, n, mb, d_out);
+}
+
 inline const OzlCurveOps* curve_ops_for(int curve) {
   switch (curve) {
     case OZL_BLS12_381_G1: return &ozl_ops_bls12_381_g1;
@@ -491,9 +555,88 @@ inline int ozl_rt_msm(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bas
   return ops->msm(ctx, ws, st, b, d_scalars, n, d_out);
 }
 
+// Point-range batches for an MSM whose scalars start in HOST memory.  The first batch is small (its
+// copy is the only part of the transfer nothing can hide), later ones grow no faster than the ratio
+// of accumulation time to copy time: ~9:1 for page-locked memory on one GPU (56 GB/s against 2e8
+// points/s), ~3.5:1 with eight GPUs pulling through one host, ~1.5:1 for pageable memory.
+// OZL_MSM_H2D_SPLIT="f0,f1,..." overrides the fractions (the last batch takes the remainder).
+inline void plan_host_batches(size_t n, bool pinned, MsmBatches& mb) {
+  static const std::vector<double> forced = []() {
+    std::vector<double> v;
+    if (const char* e = getenv("OZL_MSM_H2D_SPLIT")) {
+      const char* q = e;
+      while (*q && (int)v.size() < MSM_MAX_BATCHES - 1) {
+        char* end = nullptr;
+        double f = strtod(q, &end);
+        if (end == q) break;
+        if (f > 0) v.push_back(f);
+        q = *end ? end + 1 : end;
+      }
+    }
+    return v;
+  }();
+  std::vector<double> fr;
+  if (!forced.empty()) fr = forced;
+  else if (n < ((size_t)1 << 22)) fr = {};
+  else if (pinned) fr = {1.0 / 32, 7.0 / 32};
+  else fr = {1.0 / 32, 1.5 / 32, 2.25 / 32, 3.4 / 32, 5.0 / 32, 7.6 / 32};
+  mb.J = 0;
+  size_t pos = 0;
+  for (double f : fr) {
+    if (mb.J >= MSM_MAX_BATCHES - 1) break;
+    size_t k = ((size_t)(f * (double)n) + 1023) & ~(size_t)1023;
+    if (k == 0 || pos + k >= n) break;
+    mb.first[mb.J] = pos;
+    mb.count[mb.J] = k;
+    mb.J++;
+    pos += k;
+  }
+  mb.first[mb.J] = pos;
+  mb.count[mb.J] = n - pos;
+  mb.J++;
+}
+
+// MSM with HOST scalars: copies batch by batch on the context's copy stream while earlier batches are
+// being accumulated, result left in d_out (device).  *d_flags_out (device) = input-error flags.
+inline int ozl_rt_msm_host(ozl_ctx* ctx, const Bases& b, const uint64_t* scalars, size_t n, uint32_t* d_out) {
+  const OzlCurveOps* ops = curve_ops_for(b.curve);
+  if (!ops || n > b.n) return OZL_ERR_ARG;
+  int r;
+  if ((r = ensure(ctx, ctx->scalars, std::max<size_t>(n, 1) * 32))) return r;
+  if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < MSM_MAX_BATCHES; k++)
+    if (!ctx->ev_batch[k]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_batch[k], cudaEventDisableTiming));
+  bool pinned = false;
+  {
+    cudaPointerAttributes at;
+    if (n && cudaPointerGetAttributes(&at, scalars) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+    else cudaGetLastError();
+  }
+  MsmBatches mb;
+  plan_host_batches(n, pinned, mb);
+  const bool batch_affine = ctx->batch_levels > 0 || (ctx->batch_levels < 0 && batch_config().levels > 0);
+  if (batch_affine && mb.J > 1) {   // the experimental pair levels take one batch
+    mb.J = 1; mb.first[0] = 0; mb.count[0] = n;
+  }
+  mb.h_scalars = scalars;
+  mb.copy_stream = ctx->copy_stream;
+  mb.ev = ctx->ev_batch;
+  // the staging buffer may still be read by work enqueued earlier on the MSM's stream
+  if (!ctx->ev_prior) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_prior, cudaEventDisableTiming));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prior, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_prior, 0));
+  return ops->msm_batched(ctx, ctx->ws, ctx->stream, b, (const uint32_t*)ctx->scalars.p, n, mb, d_out);
+}
+
+// Reads the input-error flags the last MSM of this workspace left behind (device word) -- call after the
+// MSM's stream has been synchronized together with the result copy.
+inline const uint32_t* msm_err_flags(const MsmWorkspace& ws) { return ws.misc.p ? (const uint32_t*)ws.misc.p + 8 : nullptr; }
+
 inline void free_workspace(MsmWorkspace& ws) {
-  DevBuf* bufs[] = {&ws.counts, &ws.offsets, &ws.tile_sums, &ws.sorted, &ws.digits, &ws.partials, &ws.chunk_out, &ws.window_out, &ws.misc,
-                    &ws.lvl_off, &ws.pair_tab, &ws.pair_a, &ws.pair_b, &ws.pair_pre, &ws.lvl_pts};
+  DevBuf* bufs[] = {&ws.counts, &ws.tile_sums, &ws.sorted, &ws.digits, &ws.chunk_out, &ws.window_out, &ws.misc,
+                    &ws.lvl_off, &ws.pair_tab, &ws.pair_a, &ws.pair_b, &ws.pair_pre, &ws.lvl_pts,
+                    &ws.offsets[0], &ws.offsets[1], &ws.offsets[2], &ws.offsets[3], &ws.offsets[4], &ws.offsets[5], &ws.offsets[6], &ws.offsets[7],
+                    &ws.partials[0], &ws.partials[1], &ws.partials[2], &ws.partials[3], &ws.partials[4], &ws.partials[5], &ws.partials[6], &ws.partials[7]};
   for (DevBuf* b : bufs)
     if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
 }

@@ -8,8 +8,11 @@
   SpMVs for a_j/b_j/c_j, fixed-base scalar multiplications).  Setup is not the hot path.
 * ``Groth16.prove(pk, z, rng)``   ~ ``ProofSystem::prove`` (groth16.rs:446-457): draws r, s like
   ``create_random_proof`` and runs ``ozl_groth16_prove`` (device witness map + 5 MSMs).
-* ``verify`` stays with arkworks on the CPU in the reference (3 pairings, milliseconds;
-  groth16.rs:460-466) and is not accelerated here; tests check proofs with the oracle.
+* ``Groth16.verify(vk, input, proof)`` ~ ``ProofSystem::verify`` (groth16.rs:459-466): host-side, like the
+  reference (three pairings, milliseconds; SURVEY.md row a-6 keeps it off the GPU).  The pairing is
+  ``openzl_b200.pairing`` (optimal ate over the Fq2/Fq6/Fq12 tower).
+* ``ProvingContext.encode`` / ``Groth16.proving_context_from_bytes`` ~ ``ProvingContext::{encode, decode}``
+  (groth16.rs:142-179): ark's uncompressed, unchecked ``ProvingKey`` bytes <-> device-resident MSM bases.
 """
 from __future__ import annotations
 
@@ -21,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from .circuits.r1cs import Csr, R1CS
-from .context import Context
+from .context import Bases, Context
 
 PAIRINGS = {
     "bn254": dict(id=0, g1=_lib.BN254_G1, g2=_lib.BN254_G2, fr=_lib.BN254_FR,
@@ -73,11 +76,44 @@ class Trapdoor:
 
 @dataclass
 class VerifyingData:
-    """What a verifier needs, kept as scalars because the trapdoor is known in this harness:
-    ic[j] = (beta a_j + alpha b_j + c_j) / gamma for the instance variables."""
+    """``VerifyingContext`` (groth16.rs:183-186): the verifying key as affine points in the C ABI's
+    layout (Montgomery limbs), ``gamma_abc_g1[j] = [(beta a_j + alpha b_j + c_j) / gamma] G1`` for the
+    instance variables.  A key made by the known-trapdoor ``compile`` also records the trapdoor and the
+    ``ic`` scalars (harness only: tests compare proofs with their discrete logs); a key decoded from
+    bytes has neither."""
     pairing: str
-    trapdoor: Trapdoor
-    ic: List[int]
+    trapdoor: Optional[Trapdoor]
+    ic: Optional[List[int]]
+    alpha_g1: Optional[np.ndarray] = None
+    beta_g2: Optional[np.ndarray] = None
+    gamma_g2: Optional[np.ndarray] = None
+    delta_g2: Optional[np.ndarray] = None
+    gamma_abc_g1: Optional[np.ndarray] = None      # (n_instance, 2 * limbs)
+
+    def to_serializable(self):
+        from . import serialize as ser
+        g1, g2 = ser.PAIRING_GROUPS[self.pairing]
+        return ser.VerifyingKey(ser.limbs_to_point(g1, self.alpha_g1), ser.limbs_to_point(g2, self.beta_g2),
+                                ser.limbs_to_point(g2, self.gamma_g2), ser.limbs_to_point(g2, self.delta_g2),
+                                ser.limbs_to_points(g1, self.gamma_abc_g1, _zero_rows_mask(self.gamma_abc_g1)))
+
+    def to_bytes(self) -> bytes:
+        """``VerifyingContext::encode``-style bytes: ark's compressed ``VerifyingKey``."""
+        from . import serialize as ser
+        return ser.vk_to_bytes(self.pairing, self.to_serializable())
+
+    @staticmethod
+    def from_serializable(pairing: str, vk) -> "VerifyingData":
+        from . import serialize as ser
+        g1, g2 = ser.PAIRING_GROUPS[pairing]
+        abc, _ = ser.points_to_limbs(g1, vk.gamma_abc_g1)
+        return VerifyingData(pairing, None, None, ser.point_to_limbs(g1, vk.alpha_g1), ser.point_to_limbs(g2, vk.beta_g2),
+                             ser.point_to_limbs(g2, vk.gamma_g2), ser.point_to_limbs(g2, vk.delta_g2), abc)
+
+
+def _zero_rows_mask(arr: np.ndarray) -> np.ndarray:
+    """Infinity bitset of an array of affine points in which (0, 0) encodes the identity."""
+    return np.packbits(~np.asarray(arr).reshape(len(arr), -1).any(axis=1), bitorder="little")
 
 
 @dataclass
@@ -95,9 +131,29 @@ class Proof:
 class ProvingContext:
     """``ProvingContext<E>(ProvingKey<E>)`` resident on the device."""
 
-    def __init__(self, ctx: Context, pairing: str, handle: int, r1cs: R1CS, domain_size: int, queries=None):
+    def __init__(self, ctx: Context, pairing: str, handle: int, r1cs: R1CS, domain_size: int, queries=None,
+                 query_handles=None, vk: Optional[VerifyingData] = None, beta_g1=None, delta_g1=None):
         self.ctx, self.pairing, self.handle, self.r1cs, self.domain_size = ctx, pairing, handle, r1cs, domain_size
         self.queries = queries   # host copies of the query scalars (tests only; None when not retained)
+        self.query_handles = query_handles or {}   # bases handles owned by the device pk (kept for `encode`)
+        self.vk, self.beta_g1, self.delta_g1 = vk, beta_g1, delta_g1
+
+    def encode(self) -> bytes:
+        """``ProvingContext::encode`` (groth16.rs:163-179): ark's ``serialize_unchecked`` of the
+        ``ProvingKey`` -- the query vectors are read back from the device."""
+        from . import serialize as ser
+        g1, g2 = ser.PAIRING_GROUPS[self.pairing]
+        P = PAIRINGS[self.pairing]
+
+        def query(name, curve, g):
+            h, n = self.query_handles[name]
+            arr = Bases(self.ctx, h, curve, n).download()
+            return ser.limbs_to_points(g, arr, _zero_rows_mask(arr))
+
+        pk = ser.ProvingKey(self.vk.to_serializable(), ser.limbs_to_point(g1, self.beta_g1), ser.limbs_to_point(g1, self.delta_g1),
+                            query("a", P["g1"], g1), query("b1", P["g1"], g1), query("b2", P["g2"], g2),
+                            query("h", P["g1"], g1), query("l", P["g1"], g1))
+        return ser.proving_key_to_bytes(self.pairing, pk)
 
     def free(self):
         if self.handle:
@@ -177,20 +233,63 @@ class Groth16:
         h_h, h_l = upload(P["g1"], hq), upload(P["g1"], lq)
         consts1, _ = fixed_base_mul(ctx, P["g1"], ints_to_limbs([t.alpha, t.beta, t.delta]))
         consts2, _ = fixed_base_mul(ctx, P["g2"], ints_to_limbs([t.beta, t.delta]))
+        gamma2, _ = fixed_base_mul(ctx, P["g2"], ints_to_limbs([t.gamma]))
+        abc1, _ = fixed_base_mul(ctx, P["g1"], ints_to_limbs(ic))
+        vk = VerifyingData(pairing, t, ic, consts1[0].copy(), consts2[0].copy(), gamma2[0].copy(), consts2[1].copy(), abc1)
+        handles = dict(a=h_a, b1=h_b1, b2=h_b2, h=h_h, l=h_l)
+        pkc = Groth16._create_pk(ctx, pairing, r1cs, n, handles, consts1[0], consts1[1], consts1[2], consts2[0], consts2[1], vk)
+        pkc.queries = dict(a=a, b=b, c=c, h=hq, l=lq) if keep_queries else None
+        return pkc, vk
+
+    @staticmethod
+    def _create_pk(ctx: Context, pairing: str, r1cs: R1CS, n: int, handles, alpha1, beta1, delta1, beta2, delta2, vk):
+        P = PAIRINGS[pairing]
+        coef_m = ints_to_limbs(r1cs.coef_table, P["r"], mont=True)
         sa, ka = _csr_struct(r1cs.A)
         sb, kb = _csr_struct(r1cs.B)
         sc, kc = _csr_struct(r1cs.C)
+        alpha1, beta1, delta1, beta2, delta2 = [np.ascontiguousarray(v, dtype=np.uint64) for v in (alpha1, beta1, delta1, beta2, delta2)]
         handle = ctypes.c_uint32(0)
         ctx._check(ctx._lib.ozl_groth16_pk_create(
-            ctx._h, P["id"], nc, ni, m, ctypes.byref(sa), ctypes.byref(sb), ctypes.byref(sc), coef_m.ctypes.data,
-            coef_m.shape[0], h_a.handle, h_b1.handle, h_b2.handle, h_h.handle, h_l.handle,
-            consts1[0].ctypes.data, consts1[1].ctypes.data, consts1[2].ctypes.data, consts2[0].ctypes.data,
-            consts2[1].ctypes.data, ctypes.byref(handle)), "ozl_groth16_pk_create")
-        for hb in (h_a, h_b1, h_b2, h_h, h_l):
+            ctx._h, P["id"], r1cs.n_constraints, r1cs.n_instance, r1cs.n_vars, ctypes.byref(sa), ctypes.byref(sb), ctypes.byref(sc),
+            coef_m.ctypes.data, coef_m.shape[0], handles["a"].handle, handles["b1"].handle, handles["b2"].handle,
+            handles["h"].handle, handles["l"].handle, alpha1.ctypes.data, beta1.ctypes.data, delta1.ctypes.data,
+            beta2.ctypes.data, delta2.ctypes.data, ctypes.byref(handle)), "ozl_groth16_pk_create")
+        qh = {}
+        for name, hb in handles.items():
+            qh[name] = (hb.handle, hb.n)
             hb.handle = 0                          # ownership moved into the pk
         del ka, kb, kc
-        queries = dict(a=a, b=b, c=c, h=hq, l=lq) if keep_queries else None
-        return ProvingContext(ctx, pairing, handle.value, r1cs, n, queries), VerifyingData(pairing, t, ic)
+        return ProvingContext(ctx, pairing, handle.value, r1cs, n, None, qh, vk, beta1.copy(), delta1.copy())
+
+    @staticmethod
+    def proving_context_from_bytes(ctx: Context, pairing: str, raw: bytes, r1cs: R1CS, precompute: int = 4):
+        """``ProvingContext::decode`` (groth16.rs:142-160) onto the device: ark's unchecked, uncompressed
+        ``ProvingKey`` bytes -> five MSM bases uploads (`ozl_msm_bases_upload`, with the infinity bitsets) ->
+        a device proving key for the circuit `r1cs`.  Returns (ProvingContext, VerifyingData)."""
+        from . import serialize as ser
+        P = PAIRINGS[pairing]
+        g1, g2 = ser.PAIRING_GROUPS[pairing]
+        pk = ser.proving_key_from_bytes(pairing, raw)
+        nc, ni, m = r1cs.n_constraints, r1cs.n_instance, r1cs.n_vars
+        n = 1
+        while n < nc + ni:
+            n <<= 1
+        if (len(pk.a_query), len(pk.b_g1_query), len(pk.b_g2_query), len(pk.h_query), len(pk.l_query)) != (m, m, m, n - 1, m - ni) \
+                or len(pk.vk.gamma_abc_g1) != ni:
+            raise _lib.OzlError(1, "proving_context_from_bytes", "the key does not belong to this circuit (query lengths differ)")
+
+        def upload(curve, g, pts):
+            arr, mask = ser.points_to_limbs(g, pts)
+            hb = ctx.upload_bases(curve, arr, mask)
+            return hb.precompute(precompute) if precompute > 1 else hb
+
+        handles = dict(a=upload(P["g1"], g1, pk.a_query), b1=upload(P["g1"], g1, pk.b_g1_query), b2=upload(P["g2"], g2, pk.b_g2_query),
+                       h=upload(P["g1"], g1, pk.h_query), l=upload(P["g1"], g1, pk.l_query))
+        vk = VerifyingData.from_serializable(pairing, pk.vk)
+        pkc = Groth16._create_pk(ctx, pairing, r1cs, n, handles, vk.alpha_g1, ser.point_to_limbs(g1, pk.beta_g1),
+                                 ser.point_to_limbs(g1, pk.delta_g1), vk.beta_g2, vk.delta_g2, vk)
+        return pkc, vk
 
     @staticmethod
     def prove_with_randomness(pk: ProvingContext, z_mont: np.ndarray, r: int, s: int, want_h: bool = False):
@@ -211,10 +310,47 @@ class Groth16:
         return (proof, h) if want_h else proof
 
     @staticmethod
-    def prove(pk: ProvingContext, z_mont: np.ndarray, rng) -> Proof:
-        """``ProofSystem::prove``: r, s drawn from the caller's rng first, as ark's
-        ``create_random_proof`` does (two ``Fr::rand`` calls before any MSM)."""
+    def prove(pk: ProvingContext, z_mont: np.ndarray, rng=None) -> Proof:
+        """``ProofSystem::prove``: r, s drawn first, as ark's ``create_random_proof`` does (two
+        ``Fr::rand`` calls before any MSM), each UNIFORM in [0, r) by ark's mask-and-reject over 256 fresh
+        bits.  The reference demands ``CryptoRng`` (constraint.rs:73-79): low-entropy or predictable r, s
+        void zero-knowledge.  `rng` = None uses the operating system's CSPRNG (``secrets``); otherwise it
+        must be a cryptographic generator exposing ``randbytes(n)`` or ``getrandbits(k)`` (e.g.
+        ``random.SystemRandom``) -- numpy Generators and ``random.Random`` are refused."""
         p = PAIRINGS[pk.pairing]["r"]
-        r = int(rng.integers(0, 1 << 62)) * (1 << 192) % p if hasattr(rng, "integers") else rng.randrange(p)
-        s = int(rng.integers(0, 1 << 62)) * (1 << 190) % p if hasattr(rng, "integers") else rng.randrange(p)
+        r = _uniform_scalar(p, rng)
+        s = _uniform_scalar(p, rng)
         return Groth16.prove_with_randomness(pk, z_mont, r, s)
+
+    @staticmethod
+    def verify(vk: VerifyingData, public_inputs, proof: Proof) -> bool:
+        """``ProofSystem::verify`` (groth16.rs:459-466 -> ``verify_with_processed_vk``):
+        e(A, B) = e(alpha, beta) e(sum_j x_j gamma_abc_j, gamma) e(C, delta), x_0 = 1, on the host."""
+        from . import pairing as pr
+        return pr.groth16_verify(vk.pairing, vk.alpha_g1, vk.beta_g2, vk.gamma_g2, vk.delta_g2, vk.gamma_abc_g1,
+                                 [int(x) for x in public_inputs], proof.a, proof.b, proof.c)
+
+
+def _uniform_scalar(p: int, rng=None) -> int:
+    """ark ``UniformRand`` for a prime field: sample the limbs, mask the bits above the modulus, reject
+    values >= p.  Only cryptographic sources are accepted."""
+    import random as _random
+    import secrets
+    bits = p.bit_length()
+    if rng is None:
+        draw = lambda: secrets.randbits(bits)
+    elif isinstance(rng, _random.SystemRandom):
+        draw = lambda: rng.getrandbits(bits)
+    elif isinstance(rng, _random.Random) or hasattr(rng, "integers") or hasattr(rng, "bit_generator"):
+        raise TypeError("Groth16.prove needs a cryptographic rng (None = OS CSPRNG, or random.SystemRandom); "
+                        "use prove_with_randomness for reproducible tests")
+    elif hasattr(rng, "randbytes"):
+        draw = lambda: int.from_bytes(rng.randbytes(32), "little") & ((1 << bits) - 1)
+    elif hasattr(rng, "getrandbits"):
+        draw = lambda: rng.getrandbits(bits)
+    else:
+        raise TypeError("rng must provide randbytes(n) or getrandbits(k)")
+    while True:
+        v = draw()
+        if v < p:
+            return v

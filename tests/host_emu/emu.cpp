@@ -35,6 +35,7 @@ static void ec_op(int op, const uint32_t* a, const uint32_t* b, uint32_t k, uint
     case 1: { XYZZ<F> o; memcpy(&o, b, sizeof(o)); acc.add(o); break; }
     case 2: acc = acc.dbl(); break;
     case 3: acc = acc.mul_u32(k); break;
+    case 6: { Affine<F> p; memcpy(&p, b, sizeof(p)); acc.add_mixed_cold(p); break; }
     case 4: {  // to affine: out = x||y, returns via k? (identity -> zeros)
       Affine<F> p;
       memset(out, 0, 2 * sizeof(F));

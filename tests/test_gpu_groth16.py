@@ -144,3 +144,114 @@ def test_prove_rejects_bad_shapes(ctx):
             Groth16.prove_with_randomness(pk, np.zeros((3, 4), dtype=np.uint64), 1, 1)
     finally:
         pk.free()
+
+
+def test_prove_2p16_constraints_matches_oracle_and_verifies(ctx):
+    """188 Poseidon links = 65,424 constraints (domain 2^16): the proof of the device prover equals
+    [A']G1, [B']G2, [C']G1 from the oracle's restatement bit-for-bit, h equals the oracle's witness map
+    computed with the C++ oracle NTT, and the product's host `Groth16.verify` accepts it."""
+    links = 188
+    ch = PoseidonChain(links)
+    r1 = ch.r1cs()
+    assert r1.n_constraints == 65424
+    z = ch.assignment(2026, 1017)
+    td = _trapdoor(16)
+    pk, vk = Groth16.compile(ctx, "bn254", r1, td, keep_queries=True, precompute=32)
+    try:
+        n = pk.domain_size
+        assert n == 1 << 16
+        rnd = random.Random(4)
+        r, s = rnd.randrange(P), rnd.randrange(P)
+        z_m = ints_to_limbs(z, P, mont=True)
+        proof, h_m = Groth16.prove_with_randomness(pk, z_m, r, s, want_h=True)
+        # witness map through the oracle's C++ NTT, ark's step order (oracle/groth16.py:witness_map at speed)
+        nc, ni = r1.n_constraints, r1.n_instance
+        rows = [r1.matvec(M, z) + [0] * (n - nc) for M in (r1.A, r1.B, r1.C)]
+        for j in range(ni):
+            rows[0][nc + j] = z[j]
+        ev = []
+        for v in rows:
+            v_m = ints_to_limbs(v, P, mont=True)
+            v_m = cbind.ntt("bn254_fr", v_m, inverse=True)
+            ev.append(limbs_to_ints(cbind.ntt("bn254_fr", v_m, coset=True), P, mont=True))
+        zinv = pow((pow(5, n, P) - 1) % P, -1, P)                  # 1 / Z(g) on the coset, g = 5
+        q = [(a * b - c) * zinv % P for a, b, c in zip(*ev)]
+        h = limbs_to_ints(cbind.ntt("bn254_fr", ints_to_limbs(q, P, mont=True), inverse=True, coset=True), P, mont=True)
+        assert limbs_to_ints(h_m, P, mont=True) == h and h[n - 1] == 0
+        # proof exponents from the setup scalars the device computed (checked against the oracle at small sizes)
+        qa, qb, qc = pk.queries["a"], pk.queries["b"], pk.queries["c"]
+        m = r1.n_vars
+        dinv = pow(td.delta, -1, P)
+        zt = (pow(td.tau, n, P) - 1) % P
+        za = sum(z[j] * qa[j] for j in range(m)) % P
+        zb = sum(z[j] * qb[j] for j in range(m)) % P
+        A = (td.alpha + za + r * td.delta) % P
+        B = (td.beta + zb + s * td.delta) % P
+        l_acc = sum(z[j] * (td.beta * qa[j] + td.alpha * qb[j] + qc[j]) for j in range(ni, m)) % P * dinv % P
+        ht, tp = 0, 1
+        for i in range(n - 1):
+            ht = (ht + h[i] * tp) % P
+            tp = tp * td.tau % P
+        C = (l_acc + ht * zt % P * dinv + s * A + r * B - r * s % P * td.delta) % P
+        for name, k, got in (("bn254_g1", A, proof.a), ("bn254_g2", B, proof.b), ("bn254_g1", C, proof.c)):
+            exp, exp_inf = cbind.to_affine(name, cbind.gen_mul(name, k))
+            assert not exp_inf and (got == exp).all(), name
+        assert Groth16.verify(vk, [z[1]], proof)
+        assert not Groth16.verify(vk, [(z[1] + 1) % P], proof)
+    finally:
+        pk.free()
+
+
+def test_proving_key_bytes_to_device_round_trip(ctx):
+    """Row f-3 end to end (`ProvingContext::{encode, decode}`, groth16.rs:142-179): the device key is
+    encoded as ark's unchecked uncompressed ProvingKey bytes, decoded, re-uploaded through
+    `ozl_msm_bases_upload` (with the infinity bitsets of the b queries) and proves to the SAME proof."""
+    ch = PoseidonChain(2)
+    r1 = ch.r1cs()
+    z = ch.assignment(77, 88)
+    td = _trapdoor(33)
+    pk, vk = Groth16.compile(ctx, "bn254", r1, td)
+    pk2 = None
+    try:
+        raw = pk.encode()
+        from openzl_b200 import serialize as ser
+        g1, g2 = ser.PAIRING_GROUPS["bn254"]
+        m, n = r1.n_vars, pk.domain_size
+        s1, s2 = g1.uncompressed_size, g2.uncompressed_size
+        vk_len = s1 + 3 * s2 + 8 + r1.n_instance * s1
+        assert len(raw) == vk_len + 2 * s1 + 2 * (8 + m * s1) + (8 + m * s2) + (8 + (n - 1) * s1) + (8 + (m - r1.n_instance) * s1)
+        pk2, vk2 = Groth16.proving_context_from_bytes(ctx, "bn254", raw, r1, precompute=4)
+        assert pk2.encode() == raw
+        rnd = random.Random(8)
+        r, s = rnd.randrange(P), rnd.randrange(P)
+        z_m = ints_to_limbs(z, P, mont=True)
+        p1 = Groth16.prove_with_randomness(pk, z_m, r, s)
+        p2 = Groth16.prove_with_randomness(pk2, z_m, r, s)
+        assert (p1.a == p2.a).all() and (p1.b == p2.b).all() and (p1.c == p2.c).all()
+        assert p1.to_bytes("bn254") == p2.to_bytes("bn254")
+        assert Groth16.verify(vk2, [z[1]], p2) and Groth16.verify(vk, [z[1]], p2)
+        assert (vk2.gamma_abc_g1 == vk.gamma_abc_g1).all()
+        with pytest.raises(ozl.OzlError):          # a key for another circuit is refused
+            Groth16.proving_context_from_bytes(ctx, "bn254", raw, PoseidonChain(1).r1cs())
+        # random blinding from the OS CSPRNG still verifies (ProofSystem::prove)
+        assert Groth16.verify(vk, [z[1]], Groth16.prove(pk, z_m))
+    finally:
+        pk.free()
+        if pk2 is not None:
+            pk2.free()
+
+
+def test_pk_belongs_to_its_context_and_is_released_with_it():
+    """The pk registry lives in the context: a handle is unknown to another context, and destroying the
+    context releases proving keys the caller forgot."""
+    c1, c2 = ozl.Context(0), ozl.Context(0)
+    try:
+        r1 = PoseidonChain(1).r1cs()
+        pk, _ = Groth16.compile(c1, "bn254", r1, _trapdoor(5))
+        size = np.zeros(1, dtype=np.uint32)
+        assert c1._lib.ozl_groth16_domain_size(c1._h, pk.handle, size.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint32))) == 0
+        assert c2._lib.ozl_groth16_domain_size(c2._h, pk.handle, size.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint32))) == 5
+        assert c2._lib.ozl_groth16_pk_destroy(c2._h, pk.handle) == 5
+    finally:
+        c1.close()          # pk not freed explicitly: ozl_ctx_destroy must release it without error
+        c2.close()

@@ -180,9 +180,11 @@ def test_generated_bases_match_oracle(ctx, name):
     assert (got == exp).all()
 
 
-@pytest.mark.parametrize("log_n", [16, 20])
+@pytest.mark.parametrize("log_n", [16, 20, 22, 24])
 def test_msm_known_dlog_large(ctx, log_n):
-    """Size-independent property: for P_i = [i+1]G, sum s_i P_i = [sum s_i (i+1) mod r] G."""
+    """Size-independent property: for P_i = [i+1]G, sum s_i P_i = [sum s_i (i+1) mod r] G.
+    2^22 and 2^24 are BASELINE config 2's sweep sizes; from 2^22 up the host scalars (pageable numpy
+    memory here) reach the device in point-range batches that overlap the accumulation."""
     name = "bls12_381_g1"
     n = 1 << log_n
     r = curves.CURVES[name].fr.p
@@ -350,6 +352,109 @@ def test_msm_precompute_one_copy_per_window(ctx, name):
     try:
         info = h.info(n)
         assert info["bucket_sets"] == 1 and info["factor"] == info["windows"]
+        got, _ = gpu_affine(ctx, name, h.msm(scalars))
+        assert (got == exp).all()
+    finally:
+        h.free()
+
+
+def _known_dlog_affine(name, scalars, start, n):
+    k = cbind.dot_mod_r("bls12_381_fr", scalars, np.arange(start, start + n, dtype=np.uint64))
+    return cbind.to_affine(name, cbind.gen_mul(name, k))[0]
+
+
+@pytest.mark.parametrize("precompute", [1, 32])
+def test_msm_host_batches_pinned_pageable_device_agree(ctx, precompute):
+    """`ozl_msm` with page-locked scalars (3 batches), with pageable scalars (7 batches) and
+    `ozl_msm_device_async` with resident scalars (one batch) return the same point at 2^22, with and
+    without one shifted copy of the bases per window; a short prefix (n < uploaded count) too."""
+    import torch
+    name = "bls12_381_g1"
+    n = 1 << 22
+    r = curves.CURVES[name].fr.p
+    scalars = random_scalars(n, r, seed=77)
+    h = ctx.generate_bases(ozl.BLS12_381_G1, 5, n)
+    try:
+        if precompute > 1:
+            h.precompute(precompute)
+        exp = _known_dlog_affine(name, scalars, 5, n)
+        got_pageable, _ = gpu_affine(ctx, name, h.msm(scalars))
+        pinned = torch.from_numpy(scalars.view(np.int64)).pin_memory()
+        out = np.zeros(18, dtype=np.uint64)
+        h.msm_host_ptr(pinned.data_ptr(), n, out)
+        got_pinned, _ = gpu_affine(ctx, name, out)
+        d_s = pinned.cuda()
+        d_out = torch.zeros(18, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        h.msm_device(d_s.data_ptr(), n, d_out.data_ptr())
+        ctx.synchronize()
+        got_dev, _ = gpu_affine(ctx, name, d_out.cpu().numpy().view(np.uint64))
+        assert (got_pageable == exp).all() and (got_pinned == exp).all() and (got_dev == exp).all()
+        m = n - 12345                               # ragged prefix through the batched path
+        got_m, _ = gpu_affine(ctx, name, h.msm(scalars[:m]))
+        assert (got_m == _known_dlog_affine(name, scalars[:m], 5, m)).all()
+    finally:
+        h.free()
+
+
+def test_msm_host_batches_skewed(ctx):
+    """Batched accumulation with heavy buckets in every batch: a witness-like scalar vector (mostly
+    small values, many equal) at 2^22 through the pageable 7-batch path."""
+    name = "bls12_381_g1"
+    n = 1 << 22
+    r = curves.CURVES[name].fr.p
+    rng = np.random.default_rng(5)
+    scalars = np.zeros((n, 4), dtype=np.uint64)
+    scalars[:, 0] = rng.integers(0, 4, size=n, dtype=np.uint64)            # three quarters of the points in three buckets
+    full = random_scalars(n // 8, r, seed=6)
+    scalars[::8] = full
+    h = ctx.generate_bases(ozl.BLS12_381_G1, 1, n)
+    try:
+        got, _ = gpu_affine(ctx, name, h.msm(scalars))
+        assert (got == _known_dlog_affine(name, scalars, 1, n)).all()
+    finally:
+        h.free()
+
+
+def test_msm_rejects_non_canonical_scalars(ctx):
+    """ark's multi_scalar_mul takes any BigInteger256; this library's window plan covers canonical
+    scalars only and must say so (OZL_ERR_ARG) instead of returning a wrong point."""
+    name = "bn254_g1"
+    n = 64
+    bases = cbind.bases_seq(name, 1, n)
+    r = curves.CURVES[name].fr.p
+    scalars = random_scalars(n, r, seed=9)
+    h = ctx.upload_bases(ozl.BN254_G1, bases)
+    try:
+        h.msm(scalars)                               # canonical: fine
+        bad = scalars.copy()
+        bad[17, 3] |= np.uint64(1 << 63)             # bit 255 set: not reduced modulo r
+        with pytest.raises(ozl.OzlError) as ei:
+            h.msm(bad)
+        assert ei.value.status == 1
+        got, _ = gpu_affine(ctx, name, h.msm(scalars))      # the context stays usable
+        assert (got == oracle_affine(name, bases, scalars)[0]).all()
+    finally:
+        h.free()
+
+
+@pytest.mark.parametrize("factor", [1, 4])
+def test_msm_zero_zero_base_is_identity(ctx, factor):
+    """(0, 0) encodes the point at infinity even without an inf_mask, with and without precomputed copies."""
+    name = "bls12_381_g1"
+    n = 500
+    bases = cbind.bases_seq(name, 1, n)
+    bases[3] = 0
+    bases[499] = 0
+    scalars = directed_scalars(name, n, seed=21)
+    inf = np.zeros((n + 7) // 8, dtype=np.uint8)
+    inf[3 >> 3] |= 1 << (3 & 7)
+    inf[499 >> 3] |= 1 << (499 & 7)
+    exp, _ = oracle_affine(name, bases, scalars, inf=inf)
+    h = ctx.upload_bases(ozl.BLS12_381_G1, bases)         # no mask passed
+    try:
+        if factor > 1:
+            h.precompute(factor)
         got, _ = gpu_affine(ctx, name, h.msm(scalars))
         assert (got == exp).all()
     finally:

@@ -138,6 +138,9 @@ def test_xyzz_group_ops_match_oracle(emu, cid, name):
         out = np.zeros(4 * n32, dtype=np.uint32)
         emu.emu_ec_op(cid, 0, P(acc), P(enc_aff(B)), 0, P(out))          # mixed add
         assert to_affine(out) == c.add_affine(A, B)
+        outc = np.zeros(4 * n32, dtype=np.uint32)
+        emu.emu_ec_op(cid, 6, P(acc), P(enc_aff(B)), 0, P(outc))         # cold-path mixed add (paired products)
+        assert to_affine(outc) == c.add_affine(A, B)
         out2 = np.zeros(4 * n32, dtype=np.uint32)
         emu.emu_ec_op(cid, 1, P(acc), P(enc_xyzz_from_aff(B, rand_z())), 0, P(out2))   # full add
         assert to_affine(out2) == c.add_affine(A, B)
