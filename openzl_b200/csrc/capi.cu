@@ -366,12 +366,10 @@ int ozl_msm_submit(ozl_ctx* ctx, uint32_t handle, const uint64_t* scalars, size_
   if (r) return r;
   if (n > b->n) return OZL_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  if (!ctx->copy_stream) {
-    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; k++) {
-      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
-      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
-    }
+  if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    if (!ctx->ev_h2d[k]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
+    if (!ctx->ev_done[k]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
   }
   const int k = (int)(ctx->pipe_idx++ & 1u);
   const size_t out_bytes = 3 * coord_u32(b->curve) * 4;

@@ -341,6 +341,11 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
   const uint32_t nc = pk.n_constraints, ni = pk.n_instance, m = pk.n_vars;
   int rc;
   if (ctx->timing) stages_clear(ctx);
+  // NVTX ranges named after ark-groth16's own start_timer! labels (prover.rs / r1cs_to_qap.rs)
+  struct NvtxScope {
+    explicit NvtxScope(const char* n) { nvtxRangePushA(n); }
+    ~NvtxScope() { nvtxRangePop(); }
+  } prover_range("Groth16::Prover");
 
   STAGE(ctx, "g16_h2d_witness");
   CUDA_TRY(ctx, cudaMemcpyAsync(pk.z, z, (size_t)m * 32, cudaMemcpyHostToDevice, st));
@@ -348,6 +353,7 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
   CUDA_TRY(ctx, cudaMemcpyAsync(pk.rs + 8, s_scalar, 32, cudaMemcpyHostToDevice, st));
   STAGE_END(ctx);
 
+  nvtxRangePushA("R1CS to QAP witness map");
   STAGE(ctx, "g16_matvec");
   CUDA_TRY(ctx, cudaMemsetAsync(pk.a, 0, n * 32, st));
   CUDA_TRY(ctx, cudaMemsetAsync(pk.b, 0, n * 32, st));
@@ -382,6 +388,7 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     return cudaMemcpyAsync(dst, src, words * 4, cudaMemcpyDeviceToDevice, q);
   };
   {
+    nvtxRangePushA("Compute A / Compute B (a, b_g1, b_g2 query MSMs) + l query MSM");
     CUDA_TRY(ctx, cudaMemcpyAsync(S + 16, one, 32, cudaMemcpyHostToDevice, pk.s2));
     f->mul_canonical(pk.s2, S + 0, S + 8, S + 24);
     CUDA_TRY(ctx, cp_on(pk.s2, fs + 0, S + 8, 8));
@@ -399,6 +406,7 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, *q_l, pk.zc + (size_t)ni * 8, m - ni, acc + 1 * J1))) return rc;
     CUDA_TRY(ctx, cudaEventRecord(pk.ev_s1, pk.s1));
     CUDA_TRY(ctx, cudaEventRecord(pk.ev_s2, pk.s2));
+    nvtxRangePop();
   }
 
   STAGE(ctx, "g16_ntt");
@@ -415,11 +423,15 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
   ctx->launches += launches;
   if (ctx->timing && !ctx->stages.empty()) ctx->stages.back().launches += launches;
   STAGE_END(ctx);
+  nvtxRangePop();   // R1CS to QAP witness map
   if (h_out) CUDA_TRY(ctx, cudaMemcpyAsync(h_out, pk.a, n * 32, cudaMemcpyDeviceToHost, st));
 
   {
     // MSM outputs (Jacobian): acc[0]=h, [1]=l, [2]=a, [3]=b1 in G1 slots; b2 in a G2 slot after them
-    if ((rc = ozl_rt_msm(ctx, ctx->ws, st, *q_h, pk.hc, n - 1, acc + 0 * J1))) return rc;
+    nvtxRangePushA("Compute C (h query MSM)");
+    rc = ozl_rt_msm(ctx, ctx->ws, st, *q_h, pk.hc, n - 1, acc + 0 * J1);
+    nvtxRangePop();
+    if (rc) return rc;
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, pk.ev_s1, 0));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, pk.ev_s2, 0));
 

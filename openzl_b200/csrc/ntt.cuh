@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include "fp.cuh"
+#include "ntt_ws.h"
 
 namespace ozl {
 
@@ -31,18 +32,6 @@ struct NttConsts {
   Fp<P> g;          // coset generator g (forward) or g^-1 (inverse)
   Fp<P> g_hi;       // g^(2^lo_bits)
   Fp<P> one;
-};
-
-// Device tables are kept per direction (index 0 = forward, 1 = inverse) so a prover that
-// alternates ifft / coset_fft / coset_ifft on one domain builds each table once.
-struct NttWorkspace {
-  void* scratch = nullptr; size_t scratch_cap = 0;
-  void* tw[2] = {nullptr, nullptr}; size_t tw_cap[2] = {0, 0};
-  void* glo[2] = {nullptr, nullptr}; size_t glo_cap[2] = {0, 0};
-  void* ghi[2] = {nullptr, nullptr}; size_t ghi_cap[2] = {0, 0};
-  void* consts[2] = {nullptr, nullptr};
-  int key_field[2] = {-1, -1}, key_log_n[2] = {-1, -1};              // what tw/consts currently hold
-  int coset_key_field[2] = {-1, -1}, coset_key_log_n[2] = {-1, -1};
 };
 
 template <class P>
@@ -152,6 +141,137 @@ k_ntt_pass(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ui
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-memory tile pass: R = 3, 6 or 9 DIF stages per trip through HBM.
+//
+// A CTA of 256 threads owns a tile of 2048 elements = M x C, M = 2^R points of one sub-transform (stride
+// q = n >> (s + R) apart in memory) times C = 2048 / M neighbouring sub-transforms ("columns": consecutive
+// addresses while q >= C, consecutive blocks in the last pass where q = 1), so global traffic moves in
+// runs of C x 32 bytes (or whole columns).  The tile lives in shared memory as two planes of 16-byte
+// half-elements: eight lanes reading neighbouring columns then touch 128 contiguous bytes -> no bank
+// conflicts.  The R stages run as R / 3 rounds; in a round every thread takes one radix-8 group out of
+// the tile (elements ql = M >> (ls + 3) rows apart), does three stages in registers and puts it back.
+//
+// Code size is what bounded the register-only kernel above (ncu: sm__icc_request_hit_rate 69 %,
+// stalled_no_instruction the second largest stall, with twelve inlined multiplier bodies per pass): here the
+// stage loop is ROLLED.  Each iteration runs the four butterflies (x[i], x[i + 4]) -- four multiplier
+// bodies in the whole kernel -- and then rotates the register file by one index bit
+// (position b2 b1 b0 -> b1 b0 b2), which brings the next stage's partners to distance 4 again; three
+// rotations are the identity, so a round leaves x[] in its original order.
+// ---------------------------------------------------------------------------------------------
+static constexpr int NTT_TILE_ELEMS = 2048;
+static constexpr int NTT_TILE_THREADS = 256;
+// rows of the tile are C + 1 half-elements apart in the last pass (q = 1), where the global phases walk a
+// column: a stride of C * 16 bytes would put all eight lanes of a shared-memory phase on the same banks
+// (ncu, unpadded: 5.9e7 bank conflicts in the last pass against 8.5e6 in the others)
+static constexpr int NTT_TILE_SMEM_HALVES = NTT_TILE_ELEMS + 512;
+static constexpr int NTT_TILE_SMEM_BYTES = 2 * NTT_TILE_SMEM_HALVES * 16;
+
+template <class P>
+__global__ void __launch_bounds__(NTT_TILE_THREADS, 2)
+k_ntt_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ tw, int log_n, int s, int R,
+           int pre, int post, int last, const uint32_t* __restrict__ glo, const uint32_t* __restrict__ ghi,
+           const Fp<P>* __restrict__ scale) {
+  typedef Fp<P> F;
+  static_assert(F::N == 8, "tile layout assumes 32-byte elements");
+  extern __shared__ __align__(16) uint4 ntt_smem[];
+  uint4* plane0 = ntt_smem;                            // low 16 bytes of every element
+  uint4* plane1 = ntt_smem + NTT_TILE_SMEM_HALVES;     // high 16 bytes
+  const uint32_t n = 1u << log_n;
+  const uint32_t M = 1u << R, C = NTT_TILE_ELEMS >> R;
+  const uint32_t q = n >> (s + R);                // memory stride between the points of one sub-transform
+  const uint32_t u_base = blockIdx.x * C;         // first column: column u = blk * q + j0
+  const int lo_bits = log_n < NTT_LO_BITS ? log_n : NTT_LO_BITS;
+  const uint32_t lo_mask = (1u << lo_bits) - 1u;
+  const uint32_t tid = threadIdx.x;
+  auto col_base = [&](uint32_t c) -> uint32_t {   // memory index of point 0 of column c
+    const uint32_t u = u_base + c;
+    const uint32_t blk = u / q, j0 = u - blk * q;
+    return blk * (n >> s) + j0;
+  };
+  // thread -> tile element for the global phases: columns fastest while they are adjacent in memory
+  const bool col_major = q == 1;                  // last pass: a column is contiguous in memory, columns are M apart
+  const uint32_t RS = C + (col_major ? 1u : 0u);  // row stride of the tile in shared memory
+  // ---- load -------------------------------------------------------------------------------
+  for (uint32_t t = tid; t < NTT_TILE_ELEMS; t += NTT_TILE_THREADS) {
+    const uint32_t m = col_major ? (t & (M - 1)) : (t / C);
+    const uint32_t c = col_major ? (t >> R) : (t & (C - 1));
+    const uint32_t i = col_base(c) + m * q;
+    F v = F::load(in + (size_t)i * F::N);
+    if (pre) {
+      const F gp = F::mul_ni(F::load(ghi + (size_t)(i >> lo_bits) * F::N), F::load(glo + (size_t)(i & lo_mask) * F::N));
+      v = F::mul_ni(v, gp);
+    }
+    plane0[m * RS + c] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    plane1[m * RS + c] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+  }
+  __syncthreads();
+  // ---- rounds of three stages ---------------------------------------------------------------
+  {
+    const uint32_t c = tid & (C - 1);
+    const uint32_t rest = tid / C;                // (blkl, jl) of this thread's group: one group per thread per round
+    const uint32_t u = u_base + c;
+    const uint32_t j0 = u - (u / q) * q;
+#pragma unroll 1
+    for (int ls = 0; ls < R; ls += 3) {
+      const uint32_t ql = M >> (ls + 3);
+      const uint32_t blkl = rest / ql, jl = rest - blkl * ql;
+      const uint32_t m0 = blkl * (M >> ls) + jl;
+      F x[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t a = (m0 + (uint32_t)k * ql) * RS + c;
+        const uint4 l = plane0[a], h = plane1[a];
+        x[k].v[0] = l.x; x[k].v[1] = l.y; x[k].v[2] = l.z; x[k].v[3] = l.w;
+        x[k].v[4] = h.x; x[k].v[5] = h.y; x[k].v[6] = h.z; x[k].v[7] = h.w;
+      }
+#pragma unroll 1
+      for (int r = 0; r < 3; r++) {
+        const int sh = s + ls + r;                // global stage
+        const uint32_t kmask = (4u >> r) - 1u;    // bits of k below the stage bit
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          // position i has been rotated left r times: the group index k it holds is i rotated right r times
+          const uint32_t k = ((uint32_t)i >> r) | (((uint32_t)i << (3 - r)) & 7u);
+          const uint32_t e = ((jl + (k & kmask) * ql) * q + j0) << sh;
+          const F a = x[i], b = x[i + 4];
+          x[i] = a + b;
+          if (e == 0) {
+            x[i + 4] = a - b;
+          } else {
+            const F w = F::load(tw + (size_t)e * F::N);
+            x[i + 4] = (a - b) * w;
+          }
+        }
+        // rotate the index bits left: b2 b1 b0 -> b1 b0 b2
+        const F t1 = x[1], t2 = x[2], t3 = x[3], t4 = x[4], t5 = x[5], t6 = x[6];
+        x[2] = t1; x[4] = t2; x[6] = t3; x[1] = t4; x[3] = t5; x[5] = t6;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t a = (m0 + (uint32_t)k * ql) * RS + c;
+        plane0[a] = make_uint4(x[k].v[0], x[k].v[1], x[k].v[2], x[k].v[3]);
+        plane1[a] = make_uint4(x[k].v[4], x[k].v[5], x[k].v[6], x[k].v[7]);
+      }
+      __syncthreads();
+    }
+  }
+  // ---- store ------------------------------------------------------------------------------
+  for (uint32_t t = tid; t < NTT_TILE_ELEMS; t += NTT_TILE_THREADS) {
+    const uint32_t m = col_major ? (t & (M - 1)) : (t / C);
+    const uint32_t c = col_major ? (t >> R) : (t & (C - 1));
+    const uint32_t i = col_base(c) + m * q;
+    uint32_t k = i;
+    if (last) k = __brev(i) >> (32 - log_n);
+    const uint4 l = plane0[m * RS + c], h = plane1[m * RS + c];
+    F v;
+    v.v[0] = l.x; v.v[1] = l.y; v.v[2] = l.z; v.v[3] = l.w; v.v[4] = h.x; v.v[5] = h.y; v.v[6] = h.z; v.v[7] = h.w;
+    if (post == 1) v = F::mul_ni(v, *scale);
+    else if (post == 2) v = F::mul_ni(v, F::mul_ni(F::load(ghi + (size_t)(k >> lo_bits) * F::N), F::load(glo + (size_t)(k & lo_mask) * F::N)));
+    v.store(out + (size_t)k * F::N);
+  }
+}
+
 inline int ntt_ensure(void** p, size_t* cap, size_t bytes) {
   if (bytes <= *cap) return 0;
   if (*p) { cudaDeviceSynchronize(); cudaFree(*p); *p = nullptr; *cap = 0; }
@@ -199,13 +319,30 @@ int ntt_run(cudaStream_t st, NttWorkspace& ws, int field_id, uint32_t* d_data, u
   const uint32_t* glo = (const uint32_t*)ws.glo[dir];
   const uint32_t* ghi = (const uint32_t*)ws.ghi[dir];
 
-  // pass plan: radix-8 passes, remainder first
+  // Pass plan.  Register-only passes of 1..3 stages (k_ntt_pass) for the remainder and for small domains;
+  // shared-memory tile passes of 3, 6 or 9 stages (k_ntt_tile) for the rest: 2^24 = 9 + 9 + 6 instead of
+  // eight radix-8 trips through HBM.  OZL_NTT_TILE=0 selects the register-only plan for comparison.
+  static const bool kTile = []() { const char* e = getenv("OZL_NTT_TILE"); return !(e && e[0] == '0'); }();
   int radices[16], np = 0;
+  bool tiled[16];
   {
-    int rem = log_n % 3;
-    if (rem) radices[np++] = rem;
-    for (int i = 0; i < log_n / 3; i++) radices[np++] = 3;
+    const int rem = log_n % 3;
+    int L = log_n - rem;                       // multiple of 3
+    const bool use_tiles = kTile && log_n >= 11;   // a tile holds 2048 elements
+    if (rem) { tiled[np] = false; radices[np++] = rem; }
+    if (use_tiles) {
+      const int k = (L + 8) / 9;               // number of tile passes, as even as multiples of 3 allow
+      for (int i = 0; i < k; i++) {
+        int R = ((L / 3 + (k - i) - 1) / (k - i)) * 3;
+        tiled[np] = true; radices[np++] = R;
+        L -= R;
+      }
+    } else {
+      for (int i = 0; i < L / 3; i++) { tiled[np] = false; radices[np++] = 3; }
+    }
   }
+  // per device, so not cached in a static: a process may hold contexts on several GPUs
+  if (cudaFuncSetAttribute(k_ntt_tile<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TILE_SMEM_BYTES) != cudaSuccess) return -3;
   uint32_t* scratch = (uint32_t*)ws.scratch;
   int s = 0;
   for (int pi = 0; pi < np; pi++) {
@@ -216,13 +353,18 @@ int ntt_run(cudaStream_t st, NttWorkspace& ws, int field_id, uint32_t* d_data, u
     const int pre = (first && coset && !inverse) ? 1 : 0;
     int post = 0;
     if (lastp && inverse) post = coset ? 2 : 1;
-    const uint32_t threads = (uint32_t)(n >> R);
-    static const int kBlock = []() { const char* e = getenv("OZL_NTT_BLOCK"); int v = e ? atoi(e) : 128; return (v == 32 || v == 64 || v == 128) ? v : 128; }();
-    const uint32_t blocks = (threads + kBlock - 1) / kBlock;
-    switch (R) {
-      case 1: k_ntt_pass<P, 1><<<blocks, kBlock, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
-      case 2: k_ntt_pass<P, 2><<<blocks, kBlock, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
-      default: k_ntt_pass<P, 3><<<blocks, kBlock, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
+    if (tiled[pi]) {
+      const uint32_t blocks = (uint32_t)(n / NTT_TILE_ELEMS);
+      k_ntt_tile<P><<<blocks, NTT_TILE_THREADS, NTT_TILE_SMEM_BYTES, st>>>(src, dst, tw, log_n, s, R, pre, post, lastp, glo, ghi, &consts->size_inv);
+    } else {
+      const uint32_t threads = (uint32_t)(n >> R);
+      static const int kBlock = []() { const char* e = getenv("OZL_NTT_BLOCK"); int v = e ? atoi(e) : 128; return (v == 32 || v == 64 || v == 128) ? v : 128; }();
+      const uint32_t blocks = (threads + kBlock - 1) / kBlock;
+      switch (R) {
+        case 1: k_ntt_pass<P, 1><<<blocks, kBlock, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
+        case 2: k_ntt_pass<P, 2><<<blocks, kBlock, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
+        default: k_ntt_pass<P, 3><<<blocks, kBlock, 0, st>>>(src, dst, tw, log_n, s, pre, post, lastp, glo, ghi, &consts->size_inv); break;
+      }
     }
     (*launches)++;
     s += R;

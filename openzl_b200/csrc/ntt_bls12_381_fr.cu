@@ -1,4 +1,5 @@
 #include "runtime.cuh"
+#include "ntt.cuh"
 #include "frops.cuh"
 namespace {
 typedef ozl_params::Bls12381Fr P_;

@@ -2,6 +2,7 @@
 // bases registry, window planning, kernel sequencing and stage timing.  No CPU compute path.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: no-ops unless a profiler is attached
 
 #include <cmath>
 #include <cstdio>
@@ -15,7 +16,7 @@
 #include "params_gen.cuh"
 #include "msm.cuh"
 #include "msm_batch.cuh"
-#include "ntt.cuh"
+#include "ntt_ws.h"
 #include "curve_ops.h"
 
 using namespace ozl;
@@ -126,7 +127,10 @@ inline int ensure(ozl_ctx* ctx, DevBuf& b, size_t bytes) {
   return OZL_OK;
 }
 
+// Every pipeline stage is also an NVTX range (host-side span of the stage's launches), named like the
+// stage timers; the Groth16 prover adds ranges named after ark-groth16's own timers (groth16.cu).
 inline int stage_begin(ozl_ctx* ctx, const char* name, cudaStream_t st = nullptr, bool use_st = false) {
+  nvtxRangePushA(name);
   if (!ctx->timing) return OZL_OK;
   Stage s;
   s.name = name;
@@ -138,6 +142,7 @@ inline int stage_begin(ozl_ctx* ctx, const char* name, cudaStream_t st = nullptr
   return OZL_OK;
 }
 inline int stage_end(ozl_ctx* ctx) {
+  nvtxRangePop();
   if (!ctx->timing) return OZL_OK;
   CUDA_TRY(ctx, cudaEventRecord(ctx->stages.back().e1, ctx->stages.back().stream));
   return OZL_OK;

@@ -11,7 +11,7 @@
 //! `into_repr()` yields the canonical `BigInteger256` the MSM takes, so slices cross the boundary
 //! without conversion.  `GroupAffine` is not `repr(C)` (x, y, infinity + padding), hence the packing.
 
-pub mod groth16; // Groth16B200: ProofSystem (prove on the device, compile / verify with arkworks)
+pub mod groth16; // Groth16B200<E>: ProofSystem (prove = one ozl_groth16_prove call; compile / verify with arkworks)
 
 use ark_ec::AffineCurve;
 use ark_ff::{BigInteger256, BigInteger384, PrimeField};
@@ -22,20 +22,48 @@ pub struct OzlCtx {
     _private: [u8; 0],
 }
 
-extern "C" {
-    fn ozl_ctx_create(device: c_int, out: *mut *mut OzlCtx) -> c_int;
-    fn ozl_ctx_destroy(ctx: *mut OzlCtx);
-    fn ozl_msm_bases_upload(ctx: *mut OzlCtx, curve: c_int, bases: *const u64, inf_mask: *const u8, n: usize, handle: *mut u32) -> c_int;
-    fn ozl_msm_bases_precompute(ctx: *mut OzlCtx, handle: u32, factor: c_int) -> c_int;
-    fn ozl_msm_bases_free(ctx: *mut OzlCtx, handle: u32) -> c_int;
-    fn ozl_msm(ctx: *mut OzlCtx, handle: u32, scalars: *const u64, n: usize, out_jacobian: *mut u64) -> c_int;
-    fn ozl_ntt(ctx: *mut OzlCtx, field: c_int, data: *mut u64, log_n: u32, inverse: c_int, coset: c_int) -> c_int;
-    // multi-GPU: one process (rank) per GPU, each holding its point range of the query vector
-    fn ozl_comm_unique_id(id_out: *mut u8) -> c_int;
-    fn ozl_comm_create(ctx: *mut OzlCtx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut OzlComm) -> c_int;
-    fn ozl_comm_destroy(comm: *mut OzlComm) -> c_int;
-    fn ozl_msm_sharded(ctx: *mut OzlCtx, comm: *mut OzlComm, handle: u32, scalars: *const u64, n: usize, out_jacobian: *mut u64) -> c_int;
+/// `ozl_csr` (include/ozl.h): one R1CS matrix, coefficients as indices into a shared table.
+#[repr(C)]
+pub(crate) struct OzlCsr {
+    pub n_rows: u32,
+    pub row_ptr: *const u32,
+    pub col_idx: *const u32,
+    pub coef_idx: *const u32,
 }
+
+/// The C ABI (`include/ozl.h`), declared once for the whole crate.
+pub(crate) mod ffi {
+    use super::{OzlComm, OzlCsr, OzlCtx};
+    use std::os::raw::c_int;
+    extern "C" {
+        pub fn ozl_ctx_create(device: c_int, out: *mut *mut OzlCtx) -> c_int;
+        pub fn ozl_ctx_destroy(ctx: *mut OzlCtx);
+        pub fn ozl_msm_bases_upload(ctx: *mut OzlCtx, curve: c_int, bases: *const u64, inf_mask: *const u8, n: usize, handle: *mut u32) -> c_int;
+        pub fn ozl_msm_bases_precompute(ctx: *mut OzlCtx, handle: u32, factor: c_int) -> c_int;
+        pub fn ozl_msm_bases_free(ctx: *mut OzlCtx, handle: u32) -> c_int;
+        pub fn ozl_msm(ctx: *mut OzlCtx, handle: u32, scalars: *const u64, n: usize, out_jacobian: *mut u64) -> c_int;
+        pub fn ozl_ntt(ctx: *mut OzlCtx, field: c_int, data: *mut u64, log_n: u32, inverse: c_int, coset: c_int) -> c_int;
+        // multi-GPU: one process (rank) per GPU, each holding its point range of the query vector
+        pub fn ozl_comm_unique_id(id_out: *mut u8) -> c_int;
+        pub fn ozl_comm_create(ctx: *mut OzlCtx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut OzlComm) -> c_int;
+        pub fn ozl_comm_destroy(comm: *mut OzlComm) -> c_int;
+        pub fn ozl_msm_sharded(ctx: *mut OzlCtx, comm: *mut OzlComm, handle: u32, scalars: *const u64, n: usize, out_jacobian: *mut u64) -> c_int;
+        // Groth16 prover resident on the device
+        pub fn ozl_groth16_pk_create(
+            ctx: *mut OzlCtx, pairing: c_int, n_constraints: u32, n_instance: u32, n_vars: u32,
+            a: *const OzlCsr, b: *const OzlCsr, c: *const OzlCsr, coef_table: *const u64, n_coef: u32,
+            a_query: u32, b_g1_query: u32, b_g2_query: u32, h_query: u32, l_query: u32,
+            alpha_g1: *const u64, beta_g1: *const u64, delta_g1: *const u64, beta_g2: *const u64, delta_g2: *const u64,
+            pk_handle: *mut u32,
+        ) -> c_int;
+        pub fn ozl_groth16_pk_destroy(ctx: *mut OzlCtx, pk_handle: u32) -> c_int;
+        pub fn ozl_groth16_prove(
+            ctx: *mut OzlCtx, pk_handle: u32, z: *const u64, r: *const u64, s: *const u64,
+            proof_a: *mut u64, proof_b: *mut u64, proof_c: *mut u64, h_out: *mut u64,
+        ) -> c_int;
+    }
+}
+use ffi::*;
 
 #[repr(C)]
 pub struct OzlComm {
@@ -178,15 +206,18 @@ pub fn ntt_in_place_bn254(ctx: &Context, v: &mut [ark_bn254::Fr], inverse: bool,
     }
 }
 
-/// Curve-generic bases handle used by `groth16::Groth16B200` (BN254: 4 u64 limbs per Fq).
-pub struct Bases {
-    ctx: *mut OzlCtx,
+/// Curve-generic bases handle for stand-alone MSMs (BN254: 4 u64 limbs per Fq).  It BORROWS its context:
+/// a handle cannot outlive the context that owns its device memory (`ozl_ctx_destroy` frees every bases
+/// buffer), so the drop order of a struct's fields can no longer produce a dangling `ozl_msm_bases_free`.
+/// `groth16::Groth16B200` does not use it: there the device pk owns the five query handles.
+pub struct Bases<'c> {
+    ctx: &'c Context,
     handle: u32,
     n: usize,
 }
 
-impl Bases {
-    fn upload(ctx: &Context, curve: c_int, packed: &[u64], inf: &[u8], n: usize, precompute: i32) -> Result<Self, Error> {
+impl<'c> Bases<'c> {
+    fn upload(ctx: &'c Context, curve: c_int, packed: &[u64], inf: &[u8], n: usize, precompute: i32) -> Result<Self, Error> {
         let mut handle = 0u32;
         if unsafe { ozl_msm_bases_upload(ctx.0, curve, packed.as_ptr(), inf.as_ptr(), n, &mut handle) } != 0 {
             return Err(Error);
@@ -194,10 +225,10 @@ impl Bases {
         if precompute > 1 && unsafe { ozl_msm_bases_precompute(ctx.0, handle, precompute) } != 0 {
             return Err(Error);
         }
-        Ok(Self { ctx: ctx.0, handle, n })
+        Ok(Self { ctx, handle, n })
     }
 
-    pub fn upload_g1_bn254(ctx: &Context, bases: &[ark_bn254::G1Affine], precompute: i32) -> Result<Self, Error> {
+    pub fn upload_g1_bn254(ctx: &'c Context, bases: &[ark_bn254::G1Affine], precompute: i32) -> Result<Self, Error> {
         let mut packed = Vec::<u64>::with_capacity(bases.len() * 8);
         let mut inf = vec![0u8; (bases.len() + 7) / 8];
         for (i, p) in bases.iter().enumerate() {
@@ -212,7 +243,7 @@ impl Bases {
         Self::upload(ctx, OZL_BN254_G1, &packed, &inf, bases.len(), precompute)
     }
 
-    pub fn upload_g2_bn254(ctx: &Context, bases: &[ark_bn254::G2Affine], precompute: i32) -> Result<Self, Error> {
+    pub fn upload_g2_bn254(ctx: &'c Context, bases: &[ark_bn254::G2Affine], precompute: i32) -> Result<Self, Error> {
         let mut packed = Vec::<u64>::with_capacity(bases.len() * 16);
         let mut inf = vec![0u8; (bases.len() + 7) / 8];
         for (i, p) in bases.iter().enumerate() {
@@ -231,7 +262,7 @@ impl Bases {
     fn msm_raw<const LIMBS: usize>(&self, scalars: &[BigInteger256]) -> Result<[u64; LIMBS], Error> {
         let n = core::cmp::min(self.n, scalars.len());
         let mut out = [0u64; LIMBS];
-        match unsafe { ozl_msm(self.ctx, self.handle, scalars.as_ptr() as *const u64, n, out.as_mut_ptr()) } {
+        match unsafe { ozl_msm(self.ctx.0, self.handle, scalars.as_ptr() as *const u64, n, out.as_mut_ptr()) } {
             0 => Ok(out),
             _ => Err(Error),
         }
@@ -251,8 +282,8 @@ impl Bases {
     }
 }
 
-impl Drop for Bases {
+impl Drop for Bases<'_> {
     fn drop(&mut self) {
-        unsafe { ozl_msm_bases_free(self.ctx, self.handle) };
+        unsafe { ozl_msm_bases_free(self.ctx.0, self.handle) };
     }
 }
