@@ -100,6 +100,63 @@ struct XYZZ {
     zzz = zzz * p3;
   }
 
+  // add_mixed with its ten field products issued through out-of-line multiplier bodies, operands by value
+  // (registers).  MODE 1: ten calls of F::mul_ni; MODE 2: five calls of the paired F::mul2_ni; MODE 3: MODE 1 with
+  // the two squarings through the dedicated F::sqr_sos_ni; MODE 4: MODE 3 with the eight products through the
+  // Karatsuba body F::mul_kara_ni.  Exists because
+  // the fully inlined loop body of k_accumulate (~100 KB of SASS) does not fit the instruction cache
+  // (ncu: sm__icc_request_hit_rate 83.5 %, stalled_no_instruction 1.26 warps per issue); which variant
+  // the hot kernel uses is decided by measurement (OZL_ACC_MODE, see msm.cuh).
+  template <int MODE>
+  static OZL_DEV F mul_m(const F& a, const F& b) { return MODE >= 4 ? F::mul_kara_ni(a, b) : F::mul_ni(a, b); }
+  template <int MODE>
+  static OZL_DEV F sqr_m(const F& a) { return MODE >= 3 ? F::sqr_sos_ni(a) : F::mul_ni(a, a); }
+
+  template <int MODE>
+  OZL_DEV void add_mixed_calls(const Affine<F>& p) {
+    if (is_identity()) {
+      *this = from_affine(p);
+      return;
+    }
+    F u2, s2;
+    if (MODE == 2) {
+      typename F::Pair a = F::mul2_ni(p.x, zz, p.y, zzz);
+      u2 = a.a; s2 = a.b;
+    } else {
+      u2 = mul_m<MODE>(p.x, zz); s2 = mul_m<MODE>(p.y, zzz);
+    }
+    F pp = u2 - x;
+    F r = s2 - y;
+    if (pp.is_zero()) {
+      if (r.is_zero()) {
+        *this = dbl_affine(p);
+      } else {
+        *this = identity();
+      }
+      return;
+    }
+    if (MODE == 2) {
+      typename F::Pair b = F::sqr2_ni(pp, r);               // p2, r^2
+      typename F::Pair c = F::mul2_ni(pp, b.a, x, b.a);     // p3, q
+      F x3 = b.b - c.a - c.b.dbl();
+      typename F::Pair d = F::mul2_ni(r, c.b - x3, y, c.a);
+      typename F::Pair e = F::mul2_ni(zz, b.a, zzz, c.a);
+      y = d.a - d.b;
+      x = x3;
+      zz = e.a;
+      zzz = e.b;
+    } else {
+      F p2 = sqr_m<MODE>(pp);
+      F p3 = mul_m<MODE>(pp, p2);
+      F q = mul_m<MODE>(x, p2);
+      F x3 = sqr_m<MODE>(r) - p3 - q.dbl();
+      zz = mul_m<MODE>(zz, p2);
+      zzz = mul_m<MODE>(zzz, p3);
+      y = mul_m<MODE>(r, q - x3) - mul_m<MODE>(y, p3);
+      x = x3;
+    }
+  }
+
   // out-of-line copy of add_mixed for cold kernels (keeps their code size small)
   OZL_DEV_NOINLINE void add_mixed_cold(const Affine<F>& p) {
     if (is_identity()) {

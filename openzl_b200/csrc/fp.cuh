@@ -277,6 +277,128 @@ struct Fp {
     return r;
   }
 
+  // ---- Karatsuba product + separated Montgomery reduction -------------------------------------
+  // t[0 .. 2H) = x * y for H-limb operands, schoolbook: row i adds x_j * y_i at limb i + j as two carry
+  // chains (even j, odd j) over disjoint limb pairs, like the off-diagonal rows of sqr_sos().
+  template <int H>
+  static OZL_DEV void mul_half(const uint32_t* x, const uint32_t* y, uint32_t* t) {
+#pragma unroll
+    for (int k = 0; k < 2 * H; k++) t[k] = 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      // even chain: j = 0, 2, ..: limbs (i + j, i + j + 1); stops at limb i + H - 1 (H even), carry into limb i + H
+#pragma unroll
+      for (int j = 0; j < H; j += 2) {
+        t[i + j] = (j == 0) ? ptx::mad_lo_cc(x[j], y[i], t[i + j]) : ptx::madc_lo_cc(x[j], y[i], t[i + j]);
+        t[i + j + 1] = ptx::madc_hi_cc(x[j], y[i], t[i + j + 1]);
+      }
+      t[i + H] = ptx::addc(t[i + H], 0);
+      // odd chain: j = 1, 3, ..: limbs (i + j, i + j + 1); ends at limb i + H, whose carry out is impossible
+      // for the last row pair only through limb i + H + 1 (zero or a carry bit so far)
+#pragma unroll
+      for (int j = 1; j < H; j += 2) {
+        t[i + j] = (j == 1) ? ptx::mad_lo_cc(x[j], y[i], t[i + j]) : ptx::madc_lo_cc(x[j], y[i], t[i + j]);
+        t[i + j + 1] = ptx::madc_hi_cc(x[j], y[i], t[i + j + 1]);
+      }
+      if (i + H + 1 < 2 * H) t[i + H + 1] = ptx::addc(t[i + H + 1], 0);
+    }
+  }
+
+  // Montgomery reduction of a 2N-limb value t < p * 2^(32N): returns t / 2^(32N) mod p, fully reduced.
+  // Row i clears limb i; carries out of a chain target limbs >= N, which never feed a later multiplier m,
+  // so they are parked in cr[] (cr[k] -> limb N + k) and added once at the end.
+  static OZL_DEV Fp redc_wide(uint32_t* t) {
+    uint32_t cr[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; k++) cr[k] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const uint32_t m = ptx::mul_lo(t[i], P::INV);
+      t[i] = ptx::mad_lo_cc(P::mod()[0], m, t[i]);
+      t[i + 1] = ptx::madc_hi_cc(P::mod()[0], m, t[i + 1]);
+#pragma unroll
+      for (int j = 2; j < N; j += 2) {
+        t[i + j] = ptx::madc_lo_cc(P::mod()[j], m, t[i + j]);
+        t[i + j + 1] = ptx::madc_hi_cc(P::mod()[j], m, t[i + j + 1]);
+      }
+      cr[i] = ptx::addc(cr[i], 0);          // even chain stops at limb i + N - 1
+      t[i + 1] = ptx::mad_lo_cc(P::mod()[1], m, t[i + 1]);
+      t[i + 2] = ptx::madc_hi_cc(P::mod()[1], m, t[i + 2]);
+#pragma unroll
+      for (int j = 3; j < N; j += 2) {
+        t[i + j] = ptx::madc_lo_cc(P::mod()[j], m, t[i + j]);
+        t[i + j + 1] = ptx::madc_hi_cc(P::mod()[j], m, t[i + j + 1]);
+      }
+      cr[i + 1] = ptx::addc(cr[i + 1], 0);  // odd chain stops at limb i + N
+    }
+    Fp r;
+    r.v[0] = ptx::add_cc(t[N], cr[0]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) r.v[k] = ptx::addc_cc(t[N + k], cr[k]);
+    r.v[N - 1] = ptx::addc(t[2 * N - 1], cr[N - 1]);
+    final_sub(r.v);
+    return r;
+  }
+
+  // t[0 .. 2N) = a * b by one level of subtractive Karatsuba over halves of H = N / 2 limbs:
+  //   a b = z0 + (z0 + z2 + (a_lo - a_hi)(b_hi - b_lo)) 2^(32H) + z2 2^(64H),  z0 = a_lo b_lo, z2 = a_hi b_hi
+  // 3 H^2 wide multiplies instead of 4 H^2 (108 instead of 144 for N = 12); the differences, the signed
+  // middle term and the recombination are additions on the otherwise idle ALU pipe.
+  static OZL_DEV void mul_wide_kara(const Fp& a, const Fp& b, uint32_t* t) {
+    constexpr int H = N / 2;
+    static_assert(H % 2 == 0, "half length must be even");
+    uint32_t da[H], db[H], z1[2 * H + 1], m[2 * H];
+    // da = |a_lo - a_hi|, db = |b_hi - b_lo|, signs as all-ones masks
+    da[0] = ptx::sub_cc(a.v[0], a.v[H]);
+#pragma unroll
+    for (int i = 1; i < H; i++) da[i] = ptx::subc_cc(a.v[i], a.v[H + i]);
+    const uint32_t sa = ptx::subc(0, 0);
+    db[0] = ptx::sub_cc(b.v[H], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < H; i++) db[i] = ptx::subc_cc(b.v[H + i], b.v[i]);
+    const uint32_t sb = ptx::subc(0, 0);
+    // conditional negate: (x xor s) - s
+    da[0] = ptx::sub_cc(da[0] ^ sa, sa);
+#pragma unroll
+    for (int i = 1; i < H; i++) da[i] = ptx::subc_cc(da[i] ^ sa, sa);
+    db[0] = ptx::sub_cc(db[0] ^ sb, sb);
+#pragma unroll
+    for (int i = 1; i < H; i++) db[i] = ptx::subc_cc(db[i] ^ sb, sb);
+    mul_half<H>(a.v, b.v, t);                 // z0 -> t[0 .. 2H)
+    mul_half<H>(a.v + H, b.v + H, t + 2 * H); // z2 -> t[2H .. 4H)
+    mul_half<H>(da, db, m);
+    const uint32_t sm = sa ^ sb;              // all ones: the middle product enters negatively
+    // z1 = z0 + z2 + (+/-) m   (2H + 1 limbs, non-negative)
+    z1[0] = ptx::add_cc(t[0], t[2 * H]);
+#pragma unroll
+    for (int i = 1; i < 2 * H; i++) z1[i] = ptx::addc_cc(t[i], t[2 * H + i]);
+    z1[2 * H] = ptx::addc(0, 0);
+    // add (m xor sm) + (sm & 1), sign-extended: for sm = ~0 this is -m in two's complement over 2H + 1 limbs
+    z1[0] = ptx::add_cc(z1[0], sm & 1u);
+#pragma unroll
+    for (int i = 1; i < 2 * H; i++) z1[i] = ptx::addc_cc(z1[i], 0);
+    z1[2 * H] = ptx::addc(z1[2 * H], 0);
+    z1[0] = ptx::add_cc(z1[0], m[0] ^ sm);
+#pragma unroll
+    for (int i = 1; i < 2 * H; i++) z1[i] = ptx::addc_cc(z1[i], m[i] ^ sm);
+    z1[2 * H] = ptx::addc(z1[2 * H], sm);
+    // t += z1 * 2^(32H)
+    t[H] = ptx::add_cc(t[H], z1[0]);
+#pragma unroll
+    for (int i = 1; i <= 2 * H; i++) t[H + i] = ptx::addc_cc(t[H + i], z1[i]);
+#pragma unroll
+    for (int i = 3 * H + 1; i < 4 * H; i++) t[i] = ptx::addc_cc(t[i], 0);
+  }
+
+  // Montgomery product through Karatsuba + separated reduction; meant for the out-of-line body below
+  // (the 2N-limb intermediate costs registers the inlined hot loop does not have).
+  OZL_DEV Fp mul_kara(const Fp& b) const {
+    uint32_t t[2 * N];
+    mul_wide_kara(*this, b, t);
+    return redc_wide(t);
+  }
+  static OZL_DEV_NOINLINE Fp mul_kara_ni(Fp a, Fp b) { return a.mul_kara(b); }
+
   // Out-of-line multiplier for the cold kernels: one ~5 KB copy instead of a ~6 KB inlined body
   // per call site, so bucket reduction / Horner / inversion stay resident in the instruction cache
   // (ncu: sm__icc_request_hit_rate 50 % -> the inlined versions were instruction-fetch bound).
@@ -285,6 +407,10 @@ struct Fp {
   // them (~70 local-memory operations around a ~330-instruction body).
   static OZL_DEV_NOINLINE Fp mul_ni(Fp a, Fp b) { return a * b; }
   static OZL_DEV Fp sqr_ni(const Fp& a) { return mul_ni(a, a); }
+  // Dedicated squaring (separated operand scanning, 222 instead of 288 wide multiplies for N = 12) as its
+  // own out-of-line body: inlined into k_accumulate it lost to mul() on register pressure, out of line the
+  // pressure stays inside the callee.
+  static OZL_DEV_NOINLINE Fp sqr_sos_ni(Fp a) { return a.sqr_sos(); }
   // Two independent products in one out-of-line body.  The cold kernels (bucket reduction, window
   // sums, Horner, proof assembly) run a handful of warps per SM, so a lone multiplication is bound by
   // the 4-cycle dependent-issue latency of its carry chains; ptxas interleaves the two chains here
@@ -422,6 +548,9 @@ struct Fp2 {
     return r;
   }
   OZL_DEV Fp2 sqr_sos() const { return sqr(); }   // (test hook symmetry with Fp)
+  static OZL_DEV Fp2 sqr_sos_ni(const Fp2& a) { return sqr_ni(a); }
+  OZL_DEV Fp2 mul_kara(const Fp2& b) const { return *this * b; }
+  static OZL_DEV Fp2 mul_kara_ni(const Fp2& a, const Fp2& b) { return mul_ni(a, b); }
   // complex squaring: 2 base multiplications
   OZL_DEV Fp2 sqr() const {
     Base s = c0 + c1;

@@ -312,7 +312,9 @@ k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ so
 // loop reads indices from shared memory instead of issuing a dependent global load per point.
 static constexpr uint32_t TMA_CHUNK = 64;   // entries per lane per stage (256 B rows, 8 KB per warp)
 
-template <class F>
+// MODE 0: every field product inlined (the measured default); 1 / 2: out-of-line multiplier bodies
+// (XYZZ::add_mixed_calls), selected with OZL_ACC_MODE for the instruction-cache experiment.
+template <class F, int MODE = 0>
 __global__ void __launch_bounds__(128, (F::N <= 8 ? 4 : (F::N <= 12 ? 3 : 2)))
 k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                  uint32_t NB, uint32_t L, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials) {
@@ -378,7 +380,8 @@ k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict_
         const uint32_t e = row[k];
         Affine<F> pt = load_affine<F>(bases + (size_t)(e & 0x7fffffffu) * AFF);
         pt.y = pt.y.cneg((e >> 31) != 0);
-        acc.add_mixed(pt);
+        if (MODE == 0) acc.add_mixed(pt);
+        else acc.template add_mixed_calls<MODE>(pt);
       }
     }
     if (live) acc.store(partials + (size_t)(g + t) * XY);
@@ -416,8 +419,11 @@ k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ o
                  uint32_t heavy_t) {
   constexpr int XY = 4 * F::N;
   const uint32_t lane = threadIdx.x;
-  for (uint32_t g0 = blockIdx.x * 32; g0 < NB; g0 += gridDim.x * 32) {
-    const uint32_t g = g0 + lane;
+  // Lane l of block b looks at bucket base + b + l * gridDim.x: heavy buckets cluster (the short top window
+  // fills the LOWEST 2^k bucket ids, skewed scalars the small ones), and with 32 consecutive buckets per warp
+  // a few hundred warps did all the collapsing while the rest of the grid idled (3.98 ms at 2^26, c = 22).
+  for (uint32_t base = 0; base < NB; base += gridDim.x * 32) {
+    const uint32_t g = base + blockIdx.x + lane * gridDim.x;
     uint32_t t0 = 0, nparts = 0;
     if (g < NB) {
       const uint32_t o0 = offsets[g], o1 = offsets[g + 1];
@@ -431,7 +437,7 @@ k_collapse_heavy(uint32_t* __restrict__ partials, const uint32_t* __restrict__ o
     while (heavy) {
       const int src = __ffs(heavy) - 1;
       heavy &= heavy - 1;
-      const uint32_t hg = g0 + src;
+      const uint32_t hg = base + blockIdx.x + (uint32_t)src * gridDim.x;
       const uint32_t ht0 = __shfl_sync(0xffffffffu, t0, src);
       const uint32_t hlive = __shfl_sync(0xffffffffu, live, src);
       const uint32_t ngroups = (hlive + HEAVY_GROUP - 1) / HEAVY_GROUP;

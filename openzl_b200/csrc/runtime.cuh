@@ -475,7 +475,16 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
     } else {
       // TMA-staged index stream by default; OZL_ACC_TMA=0 selects the plain global-load variant
       static const bool use_tma = []() { const char* e = getenv("OZL_ACC_TMA"); return !(e && e[0] == '0'); }();
-      if (use_tma) k_accumulate_tma<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      // multiplier bodies of the hot loop: 0 = inlined, 1 = out-of-line mul, 2 = out-of-line paired mul, 3 = 1 + dedicated
+      // squaring.  Measured at 2^26 on B200 (BLS12-381 G1): 296.9 / 282.9 / 284.3 ms for 0 / 1 / 2 -- the inlined body
+      // (~100 KB) misses the instruction cache; BN254 G1 (8 limbs, ~45 KB) is 2 % faster inlined.
+      static const int acc_env = []() { const char* e = getenv("OZL_ACC_MODE"); return e ? atoi(e) : -1; }();
+      const int acc_mode = acc_env >= 0 ? acc_env : (F::N == 8 ? 0 : 3);
+      if (use_tma && acc_mode == 1) k_accumulate_tma<F, 1><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else if (use_tma && acc_mode == 2) k_accumulate_tma<F, 2><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else if (use_tma && acc_mode == 3) k_accumulate_tma<F, 3><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else if (use_tma && acc_mode == 4) k_accumulate_tma<F, 4><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else if (use_tma) k_accumulate_tma<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
     }
     LAUNCH_CHECK(ctx);

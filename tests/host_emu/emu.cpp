@@ -21,6 +21,7 @@ static void fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 5: r = x.sqr(); break;
     case 6: r = x.dbl(); break;
     case 7: r = x.sqr_sos(); break;
+    case 8: r = x.mul_kara(y); break;
     default: r = F::zero();
   }
   memcpy(out, &r, sizeof(F));
