@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 R381 = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this exact
 # configuration, keyed by (log2 n, window bits, base copies); other configurations report null.
-NCU_TRAFFIC = {(26, 22, 12): 157.988539e9 + 1.746420e9}
+NCU_TRAFFIC = {(26, 22, 12): 157.996512e9 + 1.748290e9}
 METRIC = "bls12_381_g1_msm_points_per_sec"
 UNIT = "points/s"
 
@@ -463,7 +463,7 @@ def run_ours(args):
         "roofline": {"kernel": "k_accumulate", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get((int(math.log2(n)), c, info["factor"])),
                      "traffic_unit": "bytes per launch",
-                     "traffic_source": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01b_ncu_k_accumulate_2p26.csv (one gather of 96 B per point per window, at 64-byte DRAM granularity)",
+                     "traffic_source": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_ncu_k_accumulate_2p26.csv (one gather of 96 B per point per window, at 64-byte DRAM granularity)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": acc,
                      "share_of_step": acc / ms_per_step},
@@ -491,6 +491,10 @@ def run_ours(args):
             line["ntt"] = ntt_block(args, 24, local_rank, 10)
         except Exception as exc:
             line["ntt"] = {"error": repr(exc)}
+        try:
+            line["g2_msm"] = g2_msm_block(args, 22, local_rank)
+        except Exception as exc:
+            line["g2_msm"] = {"error": repr(exc)}
     emit(line)
     if world > 1:
         dist.barrier()
@@ -660,6 +664,50 @@ def groth16_block(args, device_index: int = 0):
     pk.free()
     ctx.close()
     return block
+
+
+def g2_msm_block(args, log_n: int = 22, device_index: int = 0, steps: int = 4):
+    """BLS12-381 G2 MSM (the b_g2_query MSM of a BLS12-381 Groth16 proof), device-resident scalars, one
+    shifted copy of the bases per window, verified against the known discrete logs."""
+    import torch
+    import openzl_b200 as ozl
+    from oracle import cbind
+    n = 1 << log_n
+    dev = torch.device("cuda", device_index)
+    ctx = ozl.Context(device_index)
+    ctx.use_torch_stream()
+    curve = ozl.BLS12_381_G2
+    h = ctx.generate_bases(curve, 1, n)
+    h.precompute(32)
+    sc = device_scalars(n, R381, 99, dev)
+    out = torch.zeros(36, dtype=torch.int64, device=dev)
+    for _ in range(2):
+        h.msm_device(sc.data_ptr(), n, out.data_ptr())
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        h.msm_device(sc.data_ptr(), n, out.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = ctx.launch_count - l0
+    verified = None
+    if not args.no_verify:
+        k = cbind.dot_mod_r("bls12_381_fr", sc.cpu().numpy().view(np.uint64), np.arange(1, n + 1, dtype=np.uint64))
+        exp, _ = cbind.to_affine("bls12_381_g2", cbind.gen_mul("bls12_381_g2", k))
+        got, _ = ctx.jacobian_to_affine(curve, out.cpu().numpy().view(np.uint64))
+        verified = bool((got == exp).all())
+    info = h.info(n)
+    h.free()
+    del sc, out
+    ctx.close()
+    torch.cuda.empty_cache()
+    return {"metric": "bls12_381_g2_msm_points_per_sec", "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": 2,
+            "ms_per_step": ms, "config": {"workload": f"BLS12-381 G2 Pippenger MSM, 2^{log_n} points, window c={info['c']} ({info['windows']} windows "
+                                                      f"in {info['bucket_sets']} bucket sets), {info['factor']} base copies, scalars resident"},
+            "gpu_launches": int(launches), "verified_vs_known_dlog": verified}
 
 
 def run_groth16(args):

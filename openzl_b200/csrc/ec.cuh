@@ -72,7 +72,9 @@ struct XYZZ {
     return r;
   }
 
-  // this += affine p (madd-2008-s).  p must be a finite point.
+  // this += affine p (madd-2008-s).  p must be a finite point.  FUSED: y3 = r (q - x3) - y p3 as one
+  // dual product with a single Montgomery reduction (Fp::mul_add2) -- base fields only.
+  template <bool FUSED = false>
   OZL_DEV void add_mixed(const Affine<F>& p) {
     if (is_identity()) {
       *this = from_affine(p);
@@ -94,7 +96,8 @@ struct XYZZ {
     F p3 = pp * p2;
     F q = x * p2;
     F x3 = r.sqr() - p3 - q.dbl();
-    y = r * (q - x3) - y * p3;
+    if (FUSED) y = F::mul_add2(r, q - x3, y.neg(), p3);
+    else y = r * (q - x3) - y * p3;
     x = x3;
     zz = zz * p2;
     zzz = zzz * p3;
@@ -103,12 +106,13 @@ struct XYZZ {
   // add_mixed with its ten field products issued through out-of-line multiplier bodies, operands by value
   // (registers).  MODE 1: ten calls of F::mul_ni; MODE 2: five calls of the paired F::mul2_ni; MODE 3: MODE 1 with
   // the two squarings through the dedicated F::sqr_sos_ni; MODE 4: MODE 3 with the eight products through the
-  // Karatsuba body F::mul_kara_ni.  Exists because
+  // Karatsuba body F::mul_kara_ni; MODE 5: MODE 3 with y3 = r (q - x3) - y p3 as ONE fused product pair
+  // (F::mul_add2_ni: 3 N^2 instead of 4 N^2 wide multiplies, a single reduction).  Exists because
   // the fully inlined loop body of k_accumulate (~100 KB of SASS) does not fit the instruction cache
   // (ncu: sm__icc_request_hit_rate 83.5 %, stalled_no_instruction 1.26 warps per issue); which variant
   // the hot kernel uses is decided by measurement (OZL_ACC_MODE, see msm.cuh).
   template <int MODE>
-  static OZL_DEV F mul_m(const F& a, const F& b) { return MODE >= 4 ? F::mul_kara_ni(a, b) : F::mul_ni(a, b); }
+  static OZL_DEV F mul_m(const F& a, const F& b) { return MODE == 4 ? F::mul_kara_ni(a, b) : F::mul_ni(a, b); }
   template <int MODE>
   static OZL_DEV F sqr_m(const F& a) { return MODE >= 3 ? F::sqr_sos_ni(a) : F::mul_ni(a, a); }
 
@@ -152,7 +156,9 @@ struct XYZZ {
       F x3 = sqr_m<MODE>(r) - p3 - q.dbl();
       zz = mul_m<MODE>(zz, p2);
       zzz = mul_m<MODE>(zzz, p3);
-      y = mul_m<MODE>(r, q - x3) - mul_m<MODE>(y, p3);
+      // y3 = r (q - x3) - y p3: MODE 5 folds the two products into one Montgomery reduction
+      if (MODE == 5) y = F::mul_add2_ni(r, q - x3, y.neg(), p3);
+      else y = mul_m<MODE>(r, q - x3) - mul_m<MODE>(y, p3);
       x = x3;
     }
   }
@@ -177,9 +183,8 @@ struct XYZZ {
     typename F::Pair b = F::sqr2_ni(pp, r);               // p2, r^2
     typename F::Pair c = F::mul2_ni(pp, b.a, x, b.a);     // p3, q
     F x3 = b.b - c.a - c.b.dbl();
-    typename F::Pair d = F::mul2_ni(r, c.b - x3, y, c.a);
     typename F::Pair e = F::mul2_ni(zz, b.a, zzz, c.a);
-    y = d.a - d.b;
+    y = F::mul_add2_ni(r, c.b - x3, y.neg(), c.a);        // r (q - x3) - y p3, one reduction
     x = x3;
     zz = e.a;
     zzz = e.b;
@@ -207,10 +212,9 @@ struct XYZZ {
     typename F::Pair b = F::sqr2_ni(pp, r);               // p2, r^2
     typename F::Pair c = F::mul2_ni(pp, b.a, u.a, b.a);   // p3, q
     F x3 = b.b - c.a - c.b.dbl();
-    typename F::Pair d = F::mul2_ni(r, c.b - x3, s.a, c.a);
     typename F::Pair z = F::mul2_ni(zz, o.zz, zzz, o.zzz);
     typename F::Pair e = F::mul2_ni(z.a, b.a, z.b, c.a);
-    y = d.a - d.b;
+    y = F::mul_add2_ni(r, c.b - x3, s.a.neg(), c.a);      // r (q - x3) - s1 p3, one reduction
     x = x3;
     zz = e.a;
     zzz = e.b;

@@ -299,7 +299,7 @@ k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ so
         } else {
           pt.y = pt.y.cneg((e >> 31) != 0);
         }
-        acc.add_mixed(pt);   // inlined multiplier: an out-of-line one costs +26 % here (measured)
+        acc.add_mixed(pt);
       }
       acc.store(partials + (size_t)(g + t) * XY);
     }
@@ -312,10 +312,10 @@ k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ so
 // loop reads indices from shared memory instead of issuing a dependent global load per point.
 static constexpr uint32_t TMA_CHUNK = 64;   // entries per lane per stage (256 B rows, 8 KB per warp)
 
-// MODE 0: every field product inlined (the measured default); 1 / 2: out-of-line multiplier bodies
-// (XYZZ::add_mixed_calls), selected with OZL_ACC_MODE for the instruction-cache experiment.
-template <class F, int MODE = 0>
-__global__ void __launch_bounds__(128, (F::N <= 8 ? 4 : (F::N <= 12 ? 3 : 2)))
+// MODE: how the ten field products of an addition are issued (see runtime.cuh, OZL_ACC_MODE): 0 inlined,
+// 1..5 out-of-line multiplier bodies (XYZZ::add_mixed_calls), 6 inlined with the fused y3.  MINB: resident CTAs per SM.
+template <class F, int MODE = 0, int MINB = (F::N <= 8 ? 4 : (F::N <= 12 ? 3 : 2))>
+__global__ void __launch_bounds__(128, MINB)
 k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                  uint32_t NB, uint32_t L, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials) {
   constexpr int AFF = 2 * F::N;
@@ -381,6 +381,7 @@ k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict_
         Affine<F> pt = load_affine<F>(bases + (size_t)(e & 0x7fffffffu) * AFF);
         pt.y = pt.y.cneg((e >> 31) != 0);
         if (MODE == 0) acc.add_mixed(pt);
+        else if (MODE == 6) acc.template add_mixed<true>(pt);   // inlined, fused y3
         else acc.template add_mixed_calls<MODE>(pt);
       }
     }

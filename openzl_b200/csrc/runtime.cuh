@@ -475,14 +475,20 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
     } else {
       // TMA-staged index stream by default; OZL_ACC_TMA=0 selects the plain global-load variant
       static const bool use_tma = []() { const char* e = getenv("OZL_ACC_TMA"); return !(e && e[0] == '0'); }();
-      // multiplier bodies of the hot loop: 0 = inlined, 1 = out-of-line mul, 2 = out-of-line paired mul, 3 = 1 + dedicated
-      // squaring.  Measured at 2^26 on B200 (BLS12-381 G1): 296.9 / 282.9 / 284.3 ms for 0 / 1 / 2 -- the inlined body
-      // (~100 KB) misses the instruction cache; BN254 G1 (8 limbs, ~45 KB) is 2 % faster inlined.
+      // Field products of the hot loop (XYZZ::add_mixed_calls): 0 = all inlined, 1 = out-of-line mul (operands by
+      // value), 2 = out-of-line paired mul, 3 = 1 + dedicated squaring, 4 = 3 with Karatsuba products, 5 = 3 with
+      // y3 = r (q - x3) - y p3 as one fused dual product (single reduction), 6 = inlined + fused y3.
+      // Measured on B200, accumulate stage at 2^26 BLS12-381 G1: 296.9 / 282.9 / 284.3 / 277.5 / 310.4 / 260.4 ms
+      // for 0 .. 5: the inlined body (~100 KB of SASS) misses the instruction cache (ncu: icc hit rate 83.5 % ->
+      // 99.998 %, fmaheavy 85.3 % -> 92.9 %), and the fused y3 saves N^2 of the 20 N^2 wide multiplies of an addition.
       static const int acc_env = []() { const char* e = getenv("OZL_ACC_MODE"); return e ? atoi(e) : -1; }();
-      const int acc_mode = acc_env >= 0 ? acc_env : (F::N == 8 ? 0 : 3);
+      const int acc_mode = acc_env >= 0 ? acc_env : (F::N == 8 ? 6 : 5);   // BN254 G1 (8 limbs, ~45 KB inlined) is 4 % faster inlined + fused
       if (use_tma && acc_mode == 1) k_accumulate_tma<F, 1><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 2) k_accumulate_tma<F, 2><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 3) k_accumulate_tma<F, 3><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else if (use_tma && acc_mode == 13 && F::N == 12) k_accumulate_tma<F, 3, (F::N == 12 ? 4 : 2)><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);   // experiment: 4 CTAs per SM at 128 registers
+      else if (use_tma && acc_mode == 6 && F::N <= 12) k_accumulate_tma<F, (F::N <= 12 ? 6 : 0)><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else if (use_tma && acc_mode == 5) k_accumulate_tma<F, 5><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 4) k_accumulate_tma<F, 4><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma) k_accumulate_tma<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);

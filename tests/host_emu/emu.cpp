@@ -22,6 +22,14 @@ static void fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 6: r = x.dbl(); break;
     case 7: r = x.sqr_sos(); break;
     case 8: r = x.mul_kara(y); break;
+    case 9:   // x y - y (x + y) through the single-reduction form (fields with p < R / 4 only)
+      if constexpr (F::Params::BITS <= 32 * F::Params::N - 2) r = F::mul_add2_ni(x, y, y.neg(), x + y);
+      else r = x * y - y * (x + y);
+      break;
+    case 10:  // x x + y y: all four operands at their maximum when x = y = p - 1
+      if constexpr (F::Params::BITS <= 32 * F::Params::N - 2) r = F::mul_add2_ni(x, x, y, y);
+      else r = x * x + y * y;
+      break;
     default: r = F::zero();
   }
   memcpy(out, &r, sizeof(F));

@@ -60,7 +60,9 @@ def test_field_ops_match_oracle(emu, fid, f):
     pairs = [(a, b) for a in vals for b in vals] + [(rnd.randrange(f.p), rnd.randrange(f.p)) for _ in range(3000)]
     for a, b in pairs:
         for op, exp in ((0, f.mont_mul(a, b)), (1, (a + b) % f.p), (2, (a - b) % f.p), (3, (-a) % f.p),
-                        (5, f.mont_mul(a, a)), (6, (2 * a) % f.p), (7, f.mont_mul(a, a)), (8, f.mont_mul(a, b))):
+                        (5, f.mont_mul(a, a)), (6, (2 * a) % f.p), (7, f.mont_mul(a, a)), (8, f.mont_mul(a, b)),
+                        (9, (f.mont_mul(a, b) - f.mont_mul(b, (a + b) % f.p)) % f.p),
+                        (10, (f.mont_mul(a, a) + f.mont_mul(b, b)) % f.p)):
             out = np.zeros(n, dtype=np.uint32)
             emu.emu_fp_op(fid, op, P(l32(a, n)), P(l32(b, n)), P(out))
             assert f32(out) == exp, (f.name, op, hex(a), hex(b))
