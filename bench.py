@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 R381 = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this exact
 # configuration, keyed by (log2 n, window bits, base copies); other configurations report null.
-NCU_TRAFFIC = {(26, 22, 12): 157.996512e9 + 1.748290e9}
+NCU_TRAFFIC = {(26, 22, 12): 157.800895e9 + 1.624909e9}
 METRIC = "bls12_381_g1_msm_points_per_sec"
 UNIT = "points/s"
 
@@ -463,7 +463,7 @@ def run_ours(args):
         "roofline": {"kernel": "k_accumulate", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get((int(math.log2(n)), c, info["factor"])),
                      "traffic_unit": "bytes per launch",
-                     "traffic_source": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_ncu_k_accumulate_2p26.csv (one gather of 96 B per point per window, at 64-byte DRAM granularity)",
+                     "traffic_source": "bytes per launch, ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02c_ncu_k_accumulate_2p26.csv (one gather of 96 B per point per window, at 64-byte DRAM granularity)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": acc,
                      "share_of_step": acc / ms_per_step},
