@@ -42,6 +42,7 @@ R381 = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this exact
 # configuration, keyed by (log2 n, window bits, base copies); other configurations report null.
 NCU_TRAFFIC = {(26, 22, 12): 157.800895e9 + 1.624909e9}
+MUL_EQUIV_PER_MADD = 6 + 1.5 + 2 * 222.0 / 288.0    # 6 plain products, one fused pair (3/2), two dedicated squarings
 METRIC = "bls12_381_g1_msm_points_per_sec"
 UNIT = "points/s"
 
@@ -467,9 +468,13 @@ def run_ours(args):
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": acc,
                      "share_of_step": acc / ms_per_step},
-        "fma_pipe": {"note": "binding roofline: 381-bit Montgomery multiplications on the integer fma pipe",
-                     "field_mul_per_s": madds_per_s * 10, "mixed_adds_per_s": madds_per_s,
-                     "measured_mul_peak_per_s": m["mul_peak"], "frac": madds_per_s * 10 / m["mul_peak"]},
+        "fma_pipe": {"note": "binding roofline: 381-bit Montgomery multiplications on the integer fma pipe.  A mixed addition is 8 products + "
+                             "2 squarings; with y3 = r(q - x3) - y p3 fused into one reduction (3 N^2 instead of 4 N^2 wide multiplies) and the "
+                             "dedicated squaring (222 instead of 288) that is 9.04 multiplication-equivalents; ncu of the same kernel: "
+                             "sm__pipe_fmaheavy_cycles_active 90.7 % (profiles/r02c_ncu_k_accumulate_2p26.csv)",
+                     "mul_equivalents_per_mixed_add": MUL_EQUIV_PER_MADD,
+                     "field_mul_per_s": madds_per_s * MUL_EQUIV_PER_MADD, "mixed_adds_per_s": madds_per_s,
+                     "measured_mul_peak_per_s": m["mul_peak"], "frac": madds_per_s * MUL_EQUIV_PER_MADD / m["mul_peak"]},
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_acc.items()},
         "verified_vs_known_dlog": m["verified"],
     }
