@@ -257,7 +257,8 @@ uint64_t ozl_ctx_launch_count(const ozl_ctx* ctx);
 
 /* Micro-benchmark of the field multiplier that bounds every kernel here: runs `iters` dependent
  * Montgomery multiplications per thread on a full grid and returns multiplications per second.
- * field_id: 0 = BLS12-381 Fq (12 limbs), 1 = BN254 Fq (8 limbs). */
+ * field_id: 0 = BLS12-381 Fq (12 limbs), 1 = BN254 Fq (8 limbs); 2 = BLS12-381 Fq on the FP64 pipe (8 x 48-bit limbs in
+ * doubles, fp64mul.cuh), 3 = two integer and two FP64 product chains per thread (the hybrid's ceiling). */
 int ozl_bench_field_mul(ozl_ctx* ctx, int field_id, int iters, double* mul_per_sec);
 
 #ifdef __cplusplus

@@ -532,6 +532,7 @@ int ozl_bench_field_mul(ozl_ctx* ctx, int field_id, int iters, double* mul_per_s
     if (rep == 1) CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     if (field_id == 0) ozl_ops_bls12_381_g1.bench_mul(ctx->stream, blocks, threads, (uint32_t*)ctx->out.p, iters);
     else if (field_id == 1) ozl_ops_bn254_g1.bench_mul(ctx->stream, blocks, threads, (uint32_t*)ctx->out.p, iters);
+    else if (field_id >= 2 && field_id <= 4) ozl_ops_bls12_381_g1.bench_mul_fp64(ctx->stream, blocks, threads, (uint32_t*)ctx->out.p, iters, field_id - 2);
     else return OZL_ERR_ARG;
     LAUNCH_CHECK(ctx);
   }

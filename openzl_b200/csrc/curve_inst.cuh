@@ -48,6 +48,14 @@ void precompute_entry(cudaStream_t st, const uint32_t* d_src, uint32_t* d_dst, u
 void a2j_entry(cudaStream_t st, const uint32_t* d_aff, uint32_t* d_out) {
   k_affine_to_jacobian<F_><<<1, 32, 0, st>>>(d_aff, d_out);
 }
+#ifdef OZL_FP64_BENCH
+void bench_fp64_entry(cudaStream_t st, int blocks, int threads, uint32_t* d_out, int iters, int mix) {
+  k_bench_mul_fp64<OZL_BASE><<<blocks, threads, 0, st>>>(d_out, iters, mix);
+}
+#define OZL_FP64_BENCH_PTR bench_fp64_entry
+#else
+#define OZL_FP64_BENCH_PTR nullptr
+#endif
 }  // namespace
 
-const OzlCurveOps OZL_OPS = {msm_entry, msm_batched_entry, generate_entry, jsum_entry, jaff_entry, bench_entry, fixed_base_entry, lincomb_entry, smul_var_entry, smul_table_entry, build_table_entry, precompute_entry, a2j_entry};
+const OzlCurveOps OZL_OPS = {msm_entry, msm_batched_entry, generate_entry, jsum_entry, jaff_entry, bench_entry, fixed_base_entry, lincomb_entry, smul_var_entry, smul_table_entry, build_table_entry, precompute_entry, a2j_entry, OZL_FP64_BENCH_PTR};

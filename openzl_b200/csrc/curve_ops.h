@@ -38,6 +38,9 @@ struct OzlCurveOps {
   void (*precompute)(cudaStream_t st, const uint32_t* d_src, uint32_t* d_dst, uint32_t n, int shift);
   // Jacobian <- affine (x||y) on the device, for constants uploaded from the host
   void (*affine_to_jacobian)(cudaStream_t st, const uint32_t* d_aff, uint32_t* d_out_jac);
+  // base-field multiplier on the FP64 pipe (mix = 0) or two integer + two FP64 chains per thread (mix = 1); NULL where
+  // the field has no 48-bit constants
+  void (*bench_mul_fp64)(cudaStream_t st, int blocks, int threads, uint32_t* d_out, int iters, int mix);
 };
 
 extern const OzlCurveOps ozl_ops_bls12_381_g1;

@@ -9,6 +9,7 @@
 // element.  The C ABI returns ark's Jacobian (X, Y, Z) layout: (X*ZZ, Y*ZZZ, ZZ).
 #pragma once
 #include "fp.cuh"
+#include "fp64mul.cuh"
 
 namespace ozl {
 
@@ -111,6 +112,13 @@ struct XYZZ {
   // the fully inlined loop body of k_accumulate (~100 KB of SASS) does not fit the instruction cache
   // (ncu: sm__icc_request_hit_rate 83.5 %, stalled_no_instruction 1.26 warps per issue); which variant
   // the hot kernel uses is decided by measurement (OZL_ACC_MODE, see msm.cuh).
+  // product on the FP64 pipe where the field has the 48-bit constants (BLS12-381 Fq), the integer body otherwise
+  template <class G>
+  static OZL_DEV G mul_fp64_or_int(const G& a, const G& b) { return G::mul_ni(a, b); }
+  static OZL_DEV Fp<ozl_params::Bls12381Fq> mul_fp64_or_int(const Fp<ozl_params::Bls12381Fq>& a, const Fp<ozl_params::Bls12381Fq>& b) {
+    return mul_fp64_ni<ozl_params::Bls12381Fq>(a, b);
+  }
+
   template <int MODE>
   static OZL_DEV F mul_m(const F& a, const F& b) { return MODE == 4 ? F::mul_kara_ni(a, b) : F::mul_ni(a, b); }
   template <int MODE>
@@ -154,10 +162,19 @@ struct XYZZ {
       F p3 = mul_m<MODE>(pp, p2);
       F q = mul_m<MODE>(x, p2);
       F x3 = sqr_m<MODE>(r) - p3 - q.dbl();
-      zz = mul_m<MODE>(zz, p2);
-      zzz = mul_m<MODE>(zzz, p3);
-      // y3 = r (q - x3) - y p3: MODE 5 folds the two products into one Montgomery reduction
-      if (MODE == 5) y = F::mul_add2_ni(r, q - x3, y.neg(), p3);
+      // y3 = r (q - x3) - y p3: MODE >= 5 folds the two products into one Montgomery reduction.
+      // MODE 7: the two products nothing in this addition waits for (zz3, zzz3 feed the NEXT addition) run on
+      // the FP64 pipe (fp64mul.cuh) while other warps keep the integer multiplier busy.
+      if (MODE == 7) {
+        y = F::mul_add2_ni(r, q - x3, y.neg(), p3);
+        zz = mul_fp64_or_int(zz, p2);
+        zzz = mul_fp64_or_int(zzz, p3);
+      } else {
+        zz = mul_m<MODE>(zz, p2);
+        zzz = mul_m<MODE>(zzz, p3);
+      }
+      if (MODE == 7) {
+      } else if (MODE == 5) y = F::mul_add2_ni(r, q - x3, y.neg(), p3);
       else y = mul_m<MODE>(r, q - x3) - mul_m<MODE>(y, p3);
       x = x3;
     }

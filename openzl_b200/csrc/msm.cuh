@@ -873,4 +873,39 @@ __global__ void __launch_bounds__(128) k_bench_mul(uint32_t* __restrict__ out, i
   if (r.v[0] == 0x12345678u && r.v[1] == 0x9abcdef0u) r.store(out);  // never true in practice; keeps the loop alive
 }
 
+// FP64-pipe multiplier alone (mix = 0) and two integer + two FP64 chains per thread (mix = 1): the ceiling of
+// the hybrid addition (BLS12-381 Fq only).
+template <class P>
+__global__ void __launch_bounds__(128) k_bench_mul_fp64(uint32_t* __restrict__ out, int iters, int mix) {
+  typedef Fp<P> F;
+  F a = F::one(), b = F::r2();
+  a.v[0] ^= threadIdx.x;
+  b.v[1] ^= blockIdx.x;
+  F c = a + b, d = a - b;
+  if (mix == 2) {          // interleaved pair: one integer + one FP64 product per call, 2 products per call
+    for (int i = 0; i < iters; i++) {
+      FpPairIF<P> p = mul_int_fp64_pair_ni<P>(a, b, c, d);
+      a = p.i; c = p.f;
+      FpPairIF<P> q = mul_int_fp64_pair_ni<P>(b, c, d, a);
+      b = q.i; d = q.f;
+    }
+  } else if (mix) {
+    for (int i = 0; i < iters; i++) {
+      a = F::mul_ni(a, b);
+      c = mul_fp64_ni<P>(c, d);
+      b = F::mul_ni(b, c);
+      d = mul_fp64_ni<P>(d, a);
+    }
+  } else {
+    for (int i = 0; i < iters; i++) {
+      a = mul_fp64_ni<P>(a, b);
+      c = mul_fp64_ni<P>(c, d);
+      b = mul_fp64_ni<P>(b, c);
+      d = mul_fp64_ni<P>(d, a);
+    }
+  }
+  F r = a + b + c + d;
+  if (r.v[0] == 0x12345678u && r.v[1] == 0x9abcdef0u) r.store(out);
+}
+
 }  // namespace ozl

@@ -101,6 +101,22 @@ OZL_DEV void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, u
 }
 OZL_DEV void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// ---- FP64 primitives of the double-precision Montgomery product (fp64mul.cuh) -----------------
+// Every value is an exact integer held in a double.  *_rz rounds toward zero (used ON PURPOSE to cut a sum
+// at a chosen bit position); the *_x forms are exact by construction of their operands (the g++ build checks it).
+OZL_DEV double fma_rz(double a, double b, double c) { return __fma_rz(a, b, c); }
+OZL_DEV double add_rz(double a, double b) { return __dadd_rz(a, b); }
+OZL_DEV double fma_x(double a, double b, double c) { return __fma_rn(a, b, c); }
+OZL_DEV double add_x(double a, double b) { return __dadd_rn(a, b); }
+OZL_DEV double mul_x(double a, double b) { return __dmul_rn(a, b); }
+// 48-bit unsigned integer (hi16 : lo32) <-> double, through the 2^52 bias (no I2F / F2I conversions)
+OZL_DEV double u48_to_double(uint32_t lo32, uint32_t hi16) { return __dadd_rn(__hiloint2double((int)(0x43300000u | hi16), (int)lo32), -4503599627370496.0); }
+OZL_DEV void double_to_u48(double d, uint32_t& lo32, uint32_t& hi16) {
+  const double b = __dadd_rn(d, 4503599627370496.0);
+  lo32 = (uint32_t)__double2loint(b);
+  hi16 = (uint32_t)__double2hiint(b) & 0xffffu;
+}
+
 #else  // ---- g++ emulation (tests only) ----------------------------------------------------
 
 static thread_local uint32_t g_cf = 0;
@@ -126,6 +142,48 @@ inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(
 inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_hi(a, b), c); }
 inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
 inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc(mul_hi(a, b), c); }
+
+// FP64 primitives, emulated EXACTLY with 128-bit integers (all operands are integer-valued doubles below
+// 2^102); the *_x forms abort when their result would not be exactly representable, which is the property the
+// device code relies on.
+} }  // close namespaces for the includes
+#include <cstdio>
+#include <cstdlib>
+namespace ozl { namespace ptx {
+typedef __int128 emu_i128;
+inline emu_i128 emu_to_int(double d) {
+  if (d != (double)(emu_i128)d) { fprintf(stderr, "fp64 emu: non-integer operand %a\n", d); abort(); }
+  return (emu_i128)d;
+}
+inline double emu_trunc53(emu_i128 v) {     // round toward zero to 53 significant bits
+  const bool neg = v < 0;
+  unsigned __int128 m = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+  int bits = 0;
+  for (unsigned __int128 t = m; t; t >>= 1) bits++;
+  if (bits > 53) m = (m >> (bits - 53)) << (bits - 53);
+  const double r = (double)m;
+  return neg ? -r : r;
+}
+inline double emu_exact(emu_i128 v, const char* what) {
+  if (emu_trunc53(v) != (double)v || (emu_i128)(double)v != v) { fprintf(stderr, "fp64 emu: inexact %s\n", what); abort(); }
+  return (double)v;
+}
+inline double fma_rz(double a, double b, double c) { return emu_trunc53(emu_to_int(a) * emu_to_int(b) + emu_to_int(c)); }
+inline double add_rz(double a, double b) { return emu_trunc53(emu_to_int(a) + emu_to_int(b)); }
+inline double fma_x(double a, double b, double c) { return emu_exact(emu_to_int(a) * emu_to_int(b) + emu_to_int(c), "fma"); }
+inline double add_x(double a, double b) { return emu_exact(emu_to_int(a) + emu_to_int(b), "add"); }
+inline double mul_x(double a, double b) {          // b is a power of two (possibly negative exponent)
+  const double r = a * b;
+  if (r != (double)(emu_i128)r) { fprintf(stderr, "fp64 emu: scaling left a fraction\n"); abort(); }
+  return r;
+}
+inline double u48_to_double(uint32_t lo32, uint32_t hi16) { return (double)(((uint64_t)hi16 << 32) | lo32); }
+inline void double_to_u48(double d, uint32_t& lo32, uint32_t& hi16) {
+  const uint64_t v = (uint64_t)emu_to_int(d);
+  if (v >> 48) { fprintf(stderr, "fp64 emu: limb above 48 bits\n"); abort(); }
+  lo32 = (uint32_t)v;
+  hi16 = (uint32_t)(v >> 32);
+}
 
 #endif
 

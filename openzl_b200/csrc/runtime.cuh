@@ -488,6 +488,7 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
       else if (use_tma && acc_mode == 3) k_accumulate_tma<F, 3><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 13 && F::N == 12) k_accumulate_tma<F, 3, (F::N == 12 ? 4 : 2)><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);   // experiment: 4 CTAs per SM at 128 registers
       else if (use_tma && acc_mode == 6 && F::N <= 12) k_accumulate_tma<F, (F::N <= 12 ? 6 : 0)><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else if (use_tma && acc_mode == 7) k_accumulate_tma<F, 7><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 5) k_accumulate_tma<F, 5><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 4) k_accumulate_tma<F, 4><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma) k_accumulate_tma<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);

@@ -5,6 +5,7 @@
 #include <cstring>
 #include "../../openzl_b200/csrc/params_gen.cuh"
 #include "../../openzl_b200/csrc/ec.cuh"
+#include "../../openzl_b200/csrc/fp64mul.cuh"
 
 using namespace ozl;
 using namespace ozl_params;
@@ -62,6 +63,12 @@ static void ec_op(int op, const uint32_t* a, const uint32_t* b, uint32_t k, uint
 }
 
 extern "C" {
+// BLS12-381 Fq product on the emulated FP64 pipe (fp64mul.cuh); aborts if any step is inexact
+void emu_mul_fp64(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  typedef Fp<Bls12381Fq> F;
+  F r = mul_fp64<Bls12381Fq>(F::from_limbs(a), F::from_limbs(b));
+  memcpy(out, &r, sizeof(F));
+}
 // field ids: 0 Bls12381Fq, 1 Bls12381Fr, 2 Bn254Fq, 3 Bn254Fr, 4 Bls12381Fq2, 5 Bn254Fq2
 void emu_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   switch (field) {

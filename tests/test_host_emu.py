@@ -163,3 +163,23 @@ def test_xyzz_group_ops_match_oracle(emu, cid, name):
     d = c.F.degree
     J = tuple(c.F.from_coords(vals[i * d:(i + 1) * d]) for i in range(3))
     assert c.to_affine(J) == Pt
+
+
+def test_fp64_montgomery_product_matches_oracle(emu):
+    """The double-precision Montgomery product (openzl_b200/csrc/fp64mul.cuh, 8 x 48-bit limbs) equals the
+    integer one on edge values and random inputs; the g++ build emulates the FP64 primitives exactly with
+    128-bit integers and aborts on any step that would round, so passing also proves the exactness argument."""
+    f = fields.BLS12_381_FQ
+    n = 12
+    # the 48-bit constants of the header
+    limbs = [(f.p >> (48 * k)) & ((1 << 48) - 1) for k in range(8)]
+    assert limbs == [281474976688811, 194974335351294, 270634993844222, 113459389855408, 83034393350847, 73992301405303,
+                     253550359455670, 28591897852287]
+    assert (-pow(f.p, -1, 1 << 48)) % (1 << 48) == 281462091612157
+    rnd = random.Random(48)
+    vals = edge_values(f)
+    pairs = [(a, b) for a in vals for b in vals] + [(rnd.randrange(f.p), rnd.randrange(f.p)) for _ in range(20000)]
+    for a, b in pairs:
+        out = np.zeros(n, dtype=np.uint32)
+        emu.emu_mul_fp64(P(l32(a, n)), P(l32(b, n)), P(out))
+        assert f32(out) == f.mont_mul(a, b), (hex(a), hex(b))
