@@ -43,6 +43,10 @@ struct Bases {
 struct MsmWorkspace {
   DevBuf counts, tile_sums, sorted, digits, chunk_out, window_out, misc;
   DevBuf offsets[8], partials[8];     // per point-range batch (MSM_MAX_BATCHES); [0] alone for a plain MSM
+  // optional gate: the accumulation launches of an MSM on this workspace wait for this event (its digit extraction
+  // and sort do not).  The Groth16 prover holds the side-stream accumulations back until the witness-map
+  // transforms are through, because an accumulation kernel keeps every SM until its work runs out.
+  cudaEvent_t accumulate_gate = nullptr;
   // batched-affine pair levels (msm_batch.cuh): per-level offsets, chunk table, ping-pong point
   // buffers, prefix-product scratch, and the last level's point lists
   DevBuf lvl_off, pair_tab, pair_a, pair_b, pair_pre, lvl_pts;
@@ -469,6 +473,7 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
       partials = (uint32_t*)ws.partials[j].p;
     }
 
+    if (ws.accumulate_gate) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ws.accumulate_gate, 0));
     STAGE_ON(ctx, "accumulate", st);
     if (T) {
       k_accumulate<F, true><<<ctx->sm_count * 4, 128, 0, st>>>((const uint32_t*)ws.lvl_pts.p, nullptr, acc_offsets, p.NB, acc_L, work_counter, partials);
