@@ -620,6 +620,7 @@ def groth16_block(args, device_index: int = 0):
             per[name] = per.get(name, 0.0) + ms
         for k, v in per.items():
             stage_acc.setdefault(k, []).append(v)
+        timeline = [[name, round(t0_, 3), round(t1_, 3)] for name, t0_, t1_, _l in ctx.stage_spans()]
     ctx.enable_timing(False)
     stages = {k: float(np.mean(v)) for k, v in stage_acc.items()}
     # --- verification AT THIS SIZE, outside the timed region -----------------------------------
@@ -677,7 +678,7 @@ def groth16_block(args, device_index: int = 0):
         "clocks": clocks,
         "e2e": {"value": 1.0 / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(z_m.nbytes) + 64,
                 "d2h_bytes_per_step": 64 + 128 + 64, "api": "ozl_groth16_prove (C ABI, pinned host witness)"},
-        "gpu_launches": int(launches), "stages_ms": stages, "verified": verified,
+        "gpu_launches": int(launches), "stages_ms": stages, "timeline_ms": timeline, "verified": verified,
         "verified_how": "pairing equation e(A,B) = e(alpha,beta) e(IC,gamma) e(C,delta) on the timed proof at this size, product verifier (ate) "
                         "and oracle verifier (Tate) both accept it and the product rejects a wrong public input",
         "verify_s": verify_s, "concurrent": conc, "cpu_baseline": cpu,

@@ -252,6 +252,15 @@ typedef struct {
 } ozl_stage_time;
 int ozl_ctx_enable_timing(ozl_ctx* ctx, int on);
 int ozl_ctx_get_stage_times(ozl_ctx* ctx, ozl_stage_time* out, int cap);
+/* Same records as a timeline: start and end of every stage in milliseconds after the first stage's start (stages
+ * of one call run on several streams and overlap; this is the Gantt chart of the call). */
+typedef struct {
+  char name[32];
+  float start_ms;
+  float end_ms;
+  int launches;
+} ozl_stage_span;
+int ozl_ctx_get_stage_spans(ozl_ctx* ctx, ozl_stage_span* out, int cap);
 /* Total kernel launches issued by this context since creation. */
 uint64_t ozl_ctx_launch_count(const ozl_ctx* ctx);
 

@@ -28,7 +28,7 @@ EXPORTS = [
     "ozl_msm_bases_upload_device", "ozl_msm_bases_generate", "ozl_msm_bases_precompute", "ozl_msm_bases_download", "ozl_msm_bases_free",
     "ozl_msm", "ozl_msm_submit", "ozl_msm_device_async", "ozl_msm_set_window_bits", "ozl_msm_set_batch_affine", "ozl_msm_get_window_bits", "ozl_msm_bases_info", "ozl_jacobian_sum",
     "ozl_jacobian_to_affine", "ozl_ntt", "ozl_ntt_device_async", "ozl_ctx_enable_timing",
-    "ozl_ctx_get_stage_times", "ozl_ctx_launch_count", "ozl_bench_field_mul", "ozl_fr_spmv", "ozl_fr_poseidon_permute", "ozl_fixed_base_mul",
+    "ozl_ctx_get_stage_times", "ozl_ctx_get_stage_spans", "ozl_ctx_launch_count", "ozl_bench_field_mul", "ozl_fr_spmv", "ozl_fr_poseidon_permute", "ozl_fixed_base_mul",
     "ozl_groth16_pk_create", "ozl_groth16_pk_destroy", "ozl_groth16_prove", "ozl_groth16_domain_size",
     "ozl_comm_unique_id", "ozl_comm_create", "ozl_comm_destroy", "ozl_msm_sharded", "ozl_msm_sharded_device_async",
     "ozl_comm_allgather_sum_async",
@@ -55,6 +55,10 @@ class Csr(ctypes.Structure):
 
 class StageTime(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 32), ("ms", ctypes.c_float), ("launches", ctypes.c_int)]
+
+
+class StageSpan(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 32), ("start_ms", ctypes.c_float), ("end_ms", ctypes.c_float), ("launches", ctypes.c_int)]
 
 
 _lib = None
@@ -113,6 +117,7 @@ def load() -> ctypes.CDLL:
     lib.ozl_ntt_device_async.argtypes = [vp, ctypes.c_int, vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
     lib.ozl_ctx_enable_timing.argtypes = [vp, ctypes.c_int]
     lib.ozl_ctx_get_stage_times.argtypes = [vp, ctypes.POINTER(StageTime), ctypes.c_int]
+    lib.ozl_ctx_get_stage_spans.argtypes = [vp, ctypes.POINTER(StageSpan), ctypes.c_int]
     lib.ozl_ctx_launch_count.argtypes = [vp]
     lib.ozl_ctx_launch_count.restype = ctypes.c_uint64
     lib.ozl_bench_field_mul.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]

@@ -84,6 +84,14 @@ class Context:
             raise OzlError(2, "ozl_ctx_get_stage_times")
         return [(buf[i].name.decode(), float(buf[i].ms), int(buf[i].launches)) for i in range(k)]
 
+    def stage_spans(self):
+        """Timeline of the most recent timed call: (name, start_ms, end_ms, launches), offsets from the first stage."""
+        buf = (_lib.StageSpan * 96)()
+        k = self._lib.ozl_ctx_get_stage_spans(self._h, buf, 96)
+        if k < 0:
+            raise OzlError(2, "ozl_ctx_get_stage_spans")
+        return [(buf[i].name.decode(), float(buf[i].start_ms), float(buf[i].end_ms), int(buf[i].launches)) for i in range(k)]
+
     def bench_field_mul(self, field_id: int = 0, iters: int = 2000) -> float:
         out = ctypes.c_double(0.0)
         self._check(self._lib.ozl_bench_field_mul(self._h, field_id, iters, ctypes.byref(out)), "ozl_bench_field_mul")

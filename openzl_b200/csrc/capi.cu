@@ -517,6 +517,25 @@ int ozl_ctx_get_stage_times(ozl_ctx* ctx, ozl_stage_time* out, int cap) {
   return k;
 }
 
+int ozl_ctx_get_stage_spans(ozl_ctx* ctx, ozl_stage_span* out, int cap) {
+  if (!ctx || !out) return -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;   // stages live on several streams
+  int k = 0;
+  for (auto& s : ctx->stages) {
+    if (k >= cap) break;
+    float t0 = 0.f, t1 = 0.f;
+    if (cudaEventElapsedTime(&t0, ctx->stages.front().e0, s.e0) != cudaSuccess) t0 = -1.f;
+    if (cudaEventElapsedTime(&t1, ctx->stages.front().e0, s.e1) != cudaSuccess) t1 = -1.f;
+    memset(&out[k], 0, sizeof(out[k]));
+    snprintf(out[k].name, sizeof(out[k].name), "%s", s.name.c_str());
+    out[k].start_ms = t0;
+    out[k].end_ms = t1;
+    out[k].launches = s.launches;
+    k++;
+  }
+  return k;
+}
+
 uint64_t ozl_ctx_launch_count(const ozl_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int ozl_bench_field_mul(ozl_ctx* ctx, int field_id, int iters, double* mul_per_sec) {

@@ -34,8 +34,8 @@ struct Groth16Pk {
   uint32_t *acc = nullptr;        // MSM outputs + assembly scratch
   uint32_t *rs = nullptr;         // scalars for the assembly
   // the five MSMs run on three streams (main: h after the NTTs; s1: a, b1, l; s2: b2)
-  cudaStream_t s1 = nullptr, s2 = nullptr;
-  cudaEvent_t ev_z = nullptr, ev_s1 = nullptr, ev_s2 = nullptr, ev_ntt = nullptr;
+  cudaStream_t s1 = nullptr, s2 = nullptr, s3 = nullptr;   // s3: the two variable-point scalar multiples of the assembly
+  cudaEvent_t ev_z = nullptr, ev_s1 = nullptr, ev_s2 = nullptr, ev_ntt = nullptr, ev_a = nullptr, ev_b1 = nullptr, ev_s3 = nullptr, ev_fixed = nullptr;
   MsmWorkspace ws1, ws2;
 };
 
@@ -97,6 +97,9 @@ void destroy_pk(ozl_ctx* ctx, Groth16Pk* pkp) {
   free_workspace(pk.ws2);
   if (pk.s1) cudaStreamDestroy(pk.s1);
   if (pk.s2) cudaStreamDestroy(pk.s2);
+  if (pk.s3) cudaStreamDestroy(pk.s3);
+  for (cudaEvent_t e : {pk.ev_a, pk.ev_b1, pk.ev_s3, pk.ev_fixed})
+    if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {pk.ev_z, pk.ev_s1, pk.ev_s2, pk.ev_ntt}) if (e) cudaEventDestroy(e);
   delete pkp;
 }
@@ -239,8 +242,22 @@ int pk_build(ozl_ctx* ctx, Groth16Pk* pkp, const ozl_csr* A, const ozl_csr* B, c
     g2_ops(pairing)->build_byte_table(ctx->stream, pk.consts_g2 + (size_t)1 * 3 * c2, pk.tables_g2);
     ctx->launches += 5;
   }
-  CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pk.s1, cudaStreamNonBlocking));
-  CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pk.s2, cudaStreamNonBlocking));
+  {
+    // s1 carries the longest chain of a proof (a, b1, l MSMs): greatest priority, so that wherever another stream's
+    // accumulation hands an SM back (yield_ctas) the chain's kernels go first.  OZL_G16_PRIO=0: all default.
+    static const bool kPrio = []() { const char* e = getenv("OZL_G16_PRIO"); return !(e && e[0] == '0'); }();
+    static const bool kYield = []() { const char* e = getenv("OZL_G16_YIELD"); return !(e && e[0] == '0'); }();
+    int lo = 0, hi = 0;
+    CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(ctx, cudaStreamCreateWithPriority(&pk.s1, cudaStreamNonBlocking, kPrio ? hi : lo));
+    CUDA_TRY(ctx, cudaStreamCreateWithPriority(&pk.s3, cudaStreamNonBlocking, kPrio ? hi : lo));
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&pk.s2, cudaStreamNonBlocking));
+    pk.ws1.yield_ctas = pk.ws2.yield_ctas = kYield;
+  }
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_a, cudaEventDisableTiming));
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_b1, cudaEventDisableTiming));
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_s3, cudaEventDisableTiming));
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_fixed, cudaEventDisableTiming));
   CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_z, cudaEventDisableTiming));
   CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_s1, cudaEventDisableTiming));
   CUDA_TRY(ctx, cudaEventCreateWithFlags(&pk.ev_s2, cudaEventDisableTiming));
@@ -428,9 +445,23 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
   auto cp_on = [&](cudaStream_t q, uint32_t* dst, const uint32_t* src, size_t words) {
     return cudaMemcpyAsync(dst, src, words * 4, cudaMemcpyDeviceToDevice, q);
   };
+  // A and B are assembled and converted to affine where their last input appears (A on s3 after the a MSM, B on s2
+  // after the b2 MSM) instead of after the last MSM: the tail of a proof is then C alone.  OZL_G16_EARLY_AB=0: all at the end.
+  static const bool kEarlyAB = []() { const char* e = getenv("OZL_G16_EARLY_AB"); return !(e && e[0] == '0'); }();
+  static const bool kS3 = []() { const char* e = getenv("OZL_G16_S3"); return !(e && e[0] == '0'); }();
+  const bool early_ab = kEarlyAB && kS3;
+  if ((rc = ensure(ctx, ctx->out, 4096))) return rc;
+  uint32_t* const outb = (uint32_t*)ctx->out.p;
+  int* const flags = (int*)(outb + 512);
+  uint32_t* const ones = S + 80;                  // 8 unit scalars
+  uint32_t* const A_jac = acc + 8 * J1;
+  uint32_t* const C_jac = A_jac + J1;
+  uint32_t* const pts2 = acc_g2 + 2 * J2;
+  uint32_t* const B_jac = pts2 + 3 * J2;
   {
     nvtxRangePushA("Compute A / Compute B (a, b_g1, b_g2 query MSMs) + l query MSM");
     CUDA_TRY(ctx, cudaMemcpyAsync(S + 16, one, 32, cudaMemcpyHostToDevice, pk.s2));
+    for (int i = 0; i < 8; i++) CUDA_TRY(ctx, cp_on(pk.s2, ones + 8 * i, S + 16, 8));
     f->mul_canonical(pk.s2, S + 0, S + 8, S + 24);
     CUDA_TRY(ctx, cp_on(pk.s2, fs + 0, S + 8, 8));
     CUDA_TRY(ctx, cp_on(pk.s2, fs + 8, S + 0, 8));
@@ -438,13 +469,49 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     CUDA_TRY(ctx, cp_on(pk.s2, fs + 24, S + 0, 8));
     o1->scalar_mul_table(pk.s2, pk.tables_g1, fs, 4, fixed_out);
     o2->scalar_mul_table(pk.s2, pk.tables_g2, S + 8, 1, g2_fixed_out);
+    CUDA_TRY(ctx, cudaEventRecord(pk.ev_fixed, pk.s2));
     if ((rc = ozl_rt_msm(ctx, pk.ws2, pk.s2, *q_b2, pk.zc, m, acc_g2))) return rc;
+    if (early_ab) {   // B = beta2 + b2_acc + [s]delta2
+      CUDA_TRY(ctx, cp_on(pk.s2, pts2 + 0 * J2, pk.consts_g2 + 0 * J2, J2));
+      CUDA_TRY(ctx, cp_on(pk.s2, pts2 + 1 * J2, acc_g2, J2));
+      CUDA_TRY(ctx, cp_on(pk.s2, pts2 + 2 * J2, g2_fixed_out, J2));
+      o2->lincomb(pk.s2, pts2, ones, 3, B_jac);
+      o2->jacobian_to_affine(pk.s2, B_jac, outb + 4 * c1, flags + 2);
+      ctx->launches += 2;
+    }
     if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, *q_a, pk.zc, m, acc + 2 * J1))) return rc;
+    if (kS3) {
+      // [s]a_acc and [r]b1_acc (two warps, 1.25 ms of dependent doublings) leave the chain: each starts on s3 as soon
+      // as its MSM is through and runs under the next MSM of s1
+      CUDA_TRY(ctx, cudaEventRecord(pk.ev_a, pk.s1));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(pk.s3, pk.ev_a, 0));
+      CUDA_TRY(ctx, cp_on(pk.s3, vs + 0, pk.rs + 8, 8));
+      CUDA_TRY(ctx, cp_on(pk.s3, vs + 8, pk.rs + 0, 8));
+      o1->scalar_mul_var(pk.s3, acc + 2 * J1, vs, 1, var_out);
+      if (early_ab) {   // A = alpha1 + a_acc + [r]delta1
+        uint32_t* ptsA = acc + 28 * J1;
+        CUDA_TRY(ctx, cudaStreamWaitEvent(pk.s3, pk.ev_fixed, 0));
+        CUDA_TRY(ctx, cp_on(pk.s3, ptsA + 0 * J1, pk.consts_g1 + 0 * J1, J1));
+        CUDA_TRY(ctx, cp_on(pk.s3, ptsA + 1 * J1, acc + 2 * J1, J1));
+        CUDA_TRY(ctx, cp_on(pk.s3, ptsA + 2 * J1, fixed_out + 3 * J1, J1));
+        o1->lincomb(pk.s3, ptsA, ones, 3, A_jac);
+        o1->jacobian_to_affine(pk.s3, A_jac, outb, flags);
+        ctx->launches += 2;
+      }
+    }
     if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, *q_b1, pk.zc, m, acc + 3 * J1))) return rc;
-    CUDA_TRY(ctx, cp_on(pk.s1, vs + 0, pk.rs + 8, 8));
-    CUDA_TRY(ctx, cp_on(pk.s1, vs + 8, pk.rs + 0, 8));
-    o1->scalar_mul_var(pk.s1, acc + 2 * J1, vs, 2, var_out);   // acc[2] = a_acc, acc[3] = b1_acc (adjacent)
+    if (kS3) {
+      CUDA_TRY(ctx, cudaEventRecord(pk.ev_b1, pk.s1));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(pk.s3, pk.ev_b1, 0));
+      o1->scalar_mul_var(pk.s3, acc + 3 * J1, vs + 8, 1, var_out + J1);
+      CUDA_TRY(ctx, cudaEventRecord(pk.ev_s3, pk.s3));
+    } else {
+      CUDA_TRY(ctx, cp_on(pk.s1, vs + 0, pk.rs + 8, 8));
+      CUDA_TRY(ctx, cp_on(pk.s1, vs + 8, pk.rs + 0, 8));
+      o1->scalar_mul_var(pk.s1, acc + 2 * J1, vs, 2, var_out);   // acc[2] = a_acc, acc[3] = b1_acc (adjacent)
+    }
     if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, *q_l, pk.zc + (size_t)ni * 8, m - ni, acc + 1 * J1))) return rc;
+    if (kS3) CUDA_TRY(ctx, cudaStreamWaitEvent(pk.s1, pk.ev_s3, 0));   // ev_s1 then covers s3 as well
     CUDA_TRY(ctx, cudaEventRecord(pk.ev_s1, pk.s1));
     CUDA_TRY(ctx, cudaEventRecord(pk.ev_s2, pk.s2));
     nvtxRangePop();
@@ -455,7 +522,10 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
   {
     // MSM outputs (Jacobian): acc[0]=h, [1]=l, [2]=a, [3]=b1 in G1 slots; b2 in a G2 slot after them
     nvtxRangePushA("Compute C (h query MSM)");
+    const bool ws_yield = ctx->ws.yield_ctas;
+    ctx->ws.yield_ctas = pk.ws1.yield_ctas;
     rc = ozl_rt_msm(ctx, ctx->ws, st, *q_h, pk.hc, n - 1, acc + 0 * J1);
+    ctx->ws.yield_ctas = ws_yield;
     nvtxRangePop();
     if (rc) return rc;
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, pk.ev_s1, 0));
@@ -466,35 +536,29 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     // A = alpha1 + a_acc + [r]delta1 ;  B = beta2 + b2_acc + [s]delta2
     // (the scalar multiples were issued on the side streams above)
     auto cp = [&](uint32_t* dst, const uint32_t* src, size_t words) { return cp_on(st, dst, src, words); };
-    // unit-scalar sums
-    uint32_t* ones = S + 80;                // 8 unit scalars
-    for (int i = 0; i < 8; i++) CUDA_TRY(ctx, cp(ones + 8 * i, S + 16, 8));
     uint32_t* pts = acc + 20 * J1;          // up to 8 G1 points
-    uint32_t* A_jac = acc + 8 * J1;
-    uint32_t* C_jac = A_jac + J1;
-    CUDA_TRY(ctx, cp(pts + 0 * J1, pk.consts_g1 + 0 * J1, J1));   // alpha1
-    CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 2 * J1, J1));            // a_acc
-    CUDA_TRY(ctx, cp(pts + 2 * J1, fixed_out + 3 * J1, J1));      // r delta1
-    o1->lincomb(st, pts, ones, 3, A_jac);
+    if (!early_ab) {
+      CUDA_TRY(ctx, cp(pts + 0 * J1, pk.consts_g1 + 0 * J1, J1));   // alpha1
+      CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 2 * J1, J1));            // a_acc
+      CUDA_TRY(ctx, cp(pts + 2 * J1, fixed_out + 3 * J1, J1));      // r delta1
+      o1->lincomb(st, pts, ones, 3, A_jac);
+    }
     CUDA_TRY(ctx, cp(pts + 0 * J1, acc + 1 * J1, J1));            // l_acc
     CUDA_TRY(ctx, cp(pts + 1 * J1, acc + 0 * J1, J1));            // h_acc
     CUDA_TRY(ctx, cp(pts + 2 * J1, fixed_out, 3 * J1));           // s alpha1, r beta1, rs delta1
     CUDA_TRY(ctx, cp(pts + 5 * J1, var_out, 2 * J1));             // s a_acc, r b1_acc
     o1->lincomb(st, pts, ones, 7, C_jac);
-    uint32_t* pts2 = acc_g2 + 2 * J2;
-    uint32_t* B_jac = pts2 + 3 * J2;
-    CUDA_TRY(ctx, cp(pts2 + 0 * J2, pk.consts_g2 + 0 * J2, J2));  // beta2
-    CUDA_TRY(ctx, cp(pts2 + 1 * J2, acc_g2, J2));                 // b2_acc
-    CUDA_TRY(ctx, cp(pts2 + 2 * J2, g2_fixed_out, J2));           // s delta2
-    o2->lincomb(st, pts2, ones, 3, B_jac);
+    if (!early_ab) {
+      CUDA_TRY(ctx, cp(pts2 + 0 * J2, pk.consts_g2 + 0 * J2, J2));  // beta2
+      CUDA_TRY(ctx, cp(pts2 + 1 * J2, acc_g2, J2));                 // b2_acc
+      CUDA_TRY(ctx, cp(pts2 + 2 * J2, g2_fixed_out, J2));           // s delta2
+      o2->lincomb(st, pts2, ones, 3, B_jac);
+    }
     // affine outputs
-    if ((rc = ensure(ctx, ctx->out, 4096))) return rc;
-    uint32_t* outb = (uint32_t*)ctx->out.p;
-    int* flags = (int*)(outb + 512);
-    o1->jacobian_to_affine(st, A_jac, outb, flags);
+    if (!early_ab) o1->jacobian_to_affine(st, A_jac, outb, flags);
     o1->jacobian_to_affine(st, C_jac, outb + 2 * c1, flags + 1);
-    o2->jacobian_to_affine(st, B_jac, outb + 4 * c1, flags + 2);
-    ctx->launches += 10;
+    if (!early_ab) o2->jacobian_to_affine(st, B_jac, outb + 4 * c1, flags + 2);
+    ctx->launches += early_ab ? 2 : 6;
     STAGE_END(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(proof_a, outb, 2 * c1 * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(proof_c, outb + 2 * c1, 2 * c1 * 4, cudaMemcpyDeviceToHost, st));

@@ -96,11 +96,14 @@ static __global__ void k_count(const uint32_t* __restrict__ scalars, const uint8
 // [key_lo, key_hi) restricts a launch to a range of buckets: with many buckets (2^21 at c = 22) the
 // open 32-byte sectors of ALL buckets no longer fit in L2 and get evicted half-filled; scattering one
 // bucket range at a time keeps them resident at the price of re-reading the 4-byte digits.
-static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, uint32_t n, uint32_t g_base,
-                                        uint32_t idx_offset, const uint32_t* __restrict__ offsets,
-                                        uint32_t* __restrict__ cursor,
-                                        uint32_t* __restrict__ sorted, uint32_t key_lo, uint32_t key_hi) {
+template <int U>
+__global__ void __launch_bounds__(512)
+k_scatter_window(const uint32_t* __restrict__ digits_w, uint32_t n, uint32_t g_base,
+                 uint32_t idx_offset, const uint32_t* __restrict__ offsets,
+                 uint32_t* __restrict__ cursor,
+                 uint32_t* __restrict__ sorted, uint32_t key_lo, uint32_t key_hi) {
   const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt = (1u << lane) - 1u;
   // one entry: warp-aggregated cursor update (one atomic per distinct bucket per warp), then the write
   auto place = [&](uint32_t i, uint32_t d, bool valid) {
     uint32_t key = d & 0x7fffffffu;
@@ -115,23 +118,56 @@ static __global__ void k_scatter_window(const uint32_t* __restrict__ digits_w, u
       // cursor[] enters holding the bucket's count; filling from the back leaves it zeroed
       if ((uint32_t)leader == lane) base = atomicSub(&cursor[g], (uint32_t)__popc(peers));
       base = __shfl_sync(peers, base, leader);
-      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      const uint32_t rank = __popc(peers & lt);
       sorted[offsets[g] + base - 1u - rank] = (i + idx_offset) | (d & 0x80000000u);
     }
   };
-  // 16-byte loads: four digits per thread per trip (n * 4 bytes is 16-byte aligned per window when n % 4 == 0)
+  // 16-byte loads: four digits per thread per trip (n * 4 bytes is 16-byte aligned per window when n % 4 == 0).
+  // The four entries of a trip are placed TOGETHER: four peer matches, then the four returning atomics back to back,
+  // then the four writes -- one L2 round trip per trip instead of four.  That is what lets this kernel keep up with
+  // the accumulation when it runs in the four warps per SM the accumulation kernel leaves free (pipelined MSM).
   const uint32_t n4 = ((reinterpret_cast<uintptr_t>(digits_w) & 15u) == 0) ? (n >> 2) : 0;
   const uint4* d4 = reinterpret_cast<const uint4*>(digits_w);
   const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t trips = (n4 + stride - 1) / stride;           // uniform trip count keeps the warps converged
-  for (uint32_t t = 0, j = blockIdx.x * blockDim.x + threadIdx.x; t < trips; t++, j += stride) {
-    const bool valid = j < n4;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (valid) v = d4[j];
-    place(4 * j + 0, v.x, valid);
-    place(4 * j + 1, v.y, valid);
-    place(4 * j + 2, v.z, valid);
-    place(4 * j + 3, v.w, valid);
+  // U 16-byte loads are in flight per thread before the first of them is consumed (U = 2 when the kernel runs in
+  // the few warps per SM the accumulation leaves free and is bound by memory latency, not by the atomics' throughput)
+  const uint32_t trips = (n4 + U * stride - 1) / (U * stride);   // uniform trip count keeps the warps converged
+  for (uint32_t t = 0, j0 = blockIdx.x * blockDim.x + threadIdx.x; t < trips; t++, j0 += U * stride) {
+    uint4 vv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      vv[u] = make_uint4(0, 0, 0, 0);
+      if (j0 + u * stride < n4) vv[u] = d4[j0 + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t j = j0 + u * stride;
+      const uint32_t d[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+      uint32_t key[4], peers[4], base[4];
+      uint32_t any = 0;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        key[e] = d[e] & 0x7fffffffu;                              // 0 for the padding of an out-of-range j
+        if (key[e] <= key_lo || key[e] > key_hi) key[e] = 0;
+        any |= key[e];
+      }
+      if (__ballot_sync(0xffffffffu, any != 0) == 0) continue;
+#pragma unroll
+      for (int e = 0; e < 4; e++) peers[e] = __match_any_sync(0xffffffffu, key[e]);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        base[e] = 0;
+        if (key[e] && (uint32_t)(__ffs(peers[e]) - 1) == lane) base[e] = atomicSub(&cursor[g_base + key[e] - 1u], (uint32_t)__popc(peers[e]));
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        if (key[e]) {
+          const uint32_t g = g_base + key[e] - 1u;
+          const uint32_t b = __shfl_sync(peers[e], base[e], __ffs(peers[e]) - 1);
+          sorted[offsets[g] + b - 1u - __popc(peers[e] & lt)] = (4 * j + e + idx_offset) | (d[e] & 0x80000000u);
+        }
+      }
+    }
   }
   const uint32_t tail0 = n4 << 2;
   const uint32_t tail_trips = (n - tail0 + stride - 1) / stride;
@@ -313,17 +349,24 @@ k_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ so
 static constexpr uint32_t TMA_CHUNK = 64;   // entries per lane per stage (256 B rows, 8 KB per warp)
 
 // MODE: how the ten field products of an addition are issued (see runtime.cuh, OZL_ACC_MODE): 0 inlined,
-// 1..5 out-of-line multiplier bodies (XYZZ::add_mixed_calls), 6 inlined with the fused y3.  MINB: resident CTAs per SM.
-template <class F, int MODE = 0, int MINB = (F::N <= 8 ? 4 : (F::N <= 12 ? 3 : 2))>
-__global__ void __launch_bounds__(128, MINB)
-k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
-                 uint32_t NB, uint32_t L, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials) {
+// 1..5 out-of-line multiplier bodies (XYZZ::add_mixed_calls), 6 inlined with the fused y3.  NW: warps per CTA.
+// [g_lo, g_hi) restricts a launch to the slices that END at or before offsets[g_hi] and were not covered by
+// the launch of the preceding bucket interval (the slice straddling offsets[g_lo] belongs to THIS launch): the
+// pipelined MSM accumulates a bucket interval as soon as its part of the sort is complete, while the next
+// interval is still being scattered (runtime.cuh).  g_lo = 0, g_hi = NB is the whole array.
+template <class F, int MODE, int NW>
+__device__ __forceinline__ void accumulate_tma_body(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                    const uint32_t* __restrict__ offsets, uint32_t NB, uint32_t L,
+                                                    uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials,
+                                                    uint32_t g_lo, uint32_t g_hi, uint32_t max_batches) {
   constexpr int AFF = 2 * F::N;
   constexpr int XY = 4 * F::N;
-  __shared__ __align__(128) uint32_t stage[4][32][TMA_CHUNK];
-  __shared__ __align__(8) uint64_t bars[4];
+  __shared__ __align__(128) uint32_t stage[NW][32][TMA_CHUNK];
+  __shared__ __align__(8) uint64_t bars[NW];
   const uint32_t E = offsets[NB];
   const uint32_t nslices = (E + L - 1) / L;
+  const uint32_t s_lo = g_lo ? offsets[g_lo] / L : 0u;
+  const uint32_t s_hi = g_hi >= NB ? nslices : offsets[g_hi] / L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint64_t* bar = &bars[wid];
   if (lane == 0) {
@@ -333,13 +376,13 @@ k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict_
   __syncwarp();
   uint32_t parity = 0;
   uint32_t* row = &stage[wid][lane][0];
-  for (;;) {
+  for (uint32_t batch = 0; batch < max_batches; batch++) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(work_counter, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= nslices) break;
+    base = s_lo + __shfl_sync(0xffffffffu, base, 0);
+    if (base >= s_hi) break;
     const uint32_t t = base + lane;
-    const bool live = t < nslices;
+    const bool live = t < s_hi;
     const uint32_t pos = live ? t * L : 0;
     const uint32_t len = live ? min(L, E - pos) : 0;
     uint32_t g = 0, boundary = 0;
@@ -387,6 +430,35 @@ k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict_
     }
     if (live) acc.store(partials + (size_t)(g + t) * XY);
   }
+}
+
+// MINB: resident CTAs (of four warps) per SM.  max_batches: 32-slice batches a warp takes from the counter before its
+// CTA retires -- unbounded for a persistent grid of resident CTAs (a lone MSM), 1 for a grid of one CTA per four
+// batches, which hands the SM back to the block scheduler every slice (~2 ms) so that kernels of OTHER streams get
+// in by priority instead of waiting for this launch to run dry (Groth16 prover: five MSMs on four streams).
+template <class F, int MODE = 0, int MINB = (F::N <= 8 ? 4 : (F::N <= 12 ? 3 : 2))>
+__global__ void __launch_bounds__(128, MINB)
+k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                 uint32_t NB, uint32_t L, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials,
+                 uint32_t max_batches = 0xffffffffu) {
+  accumulate_tma_body<F, MODE, 4>(bases, sorted, offsets, NB, L, work_counter, partials, 0u, NB, max_batches);
+}
+
+// Interval launches of the pipelined MSM: ONE warp per CTA, so that the warps of the next interval's launch (on the
+// other accumulation stream) take over an SM's registers warp by warp as this launch runs out of slices, and a register
+// cap that leaves 4096 registers per SM free -- room for four warps of the scatter kernel that sorts the NEXT interval
+// under this one (12 x 32 x 160 for the 12-limb field, 16 x 32 x 120 for the 8-limb one; the uncapped kernels use 164 / 124).
+template <class F>
+struct AccPipe {
+  static constexpr int MAXREG = F::N <= 8 ? 120 : 160;
+  static constexpr int WARPS_PER_SM = F::N <= 8 ? 16 : 12;
+};
+template <class F, int MODE, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
+k_accumulate_tma_piece(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                       uint32_t NB, uint32_t L, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials,
+                       uint32_t g_lo, uint32_t g_hi) {
+  accumulate_tma_body<F, MODE, 1>(bases, sorted, offsets, NB, L, work_counter, partials, g_lo, g_hi, 0xffffffffu);
 }
 
 template <class F>

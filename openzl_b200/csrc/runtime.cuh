@@ -47,6 +47,17 @@ struct MsmWorkspace {
   // and sort do not).  The Groth16 prover holds the side-stream accumulations back until the witness-map
   // transforms are through, because an accumulation kernel keeps every SM until its work runs out.
   cudaEvent_t accumulate_gate = nullptr;
+  // yield: accumulation launches of this workspace use a grid of short-lived CTAs (one 32-slice batch per warp)
+  // instead of a persistent one, so that concurrent streams interleave by priority at every CTA boundary
+  bool yield_ctas = false;
+  // pipelined MSM (msm_run_batched): two high-priority streams that take the accumulation launches of alternate bucket
+  // intervals, one event per interval ("this interval is sorted") and one per stream ("its accumulations are through")
+  cudaStream_t acc_stream[2] = {nullptr, nullptr};
+  cudaStream_t sort_stream = nullptr;     // greatest priority: the scatter launches of a pipelined batch
+  cudaEvent_t ev_sort_ready = nullptr;    // "digits, counts and offsets of this batch are ready" (main stream -> sort stream)
+  cudaEvent_t ev_interval[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_acc_done[2] = {nullptr, nullptr};
   // batched-affine pair levels (msm_batch.cuh): per-level offsets, chunk table, ping-pong point
   // buffers, prefix-product scratch, and the last level's point lists
   DevBuf lvl_off, pair_tab, pair_a, pair_b, pair_pre, lvl_pts;
@@ -186,13 +197,31 @@ inline int coord_u32(int curve) {
 }
 inline int scalar_bits(int curve) { return (curve == OZL_BLS12_381_G1 || curve == OZL_BLS12_381_G2) ? 255 : 254; }
 
-inline uint32_t slice_len(uint64_t entries) {
-  uint64_t L = entries / ((uint64_t)148 * 384);
+// Accumulation threads resident on the chip: 4 / 3 / 2 CTAs of 128 threads per SM for 8 / 12 / more limbs per coordinate.
+inline uint32_t resident_acc_threads(int limbs_u32, int sm_count = 148) {
+  return (uint32_t)sm_count * 128u * (limbs_u32 <= 8 ? 4u : (limbs_u32 <= 12 ? 3u : 2u));
+}
+// Entries per accumulation thread: 128 when there is enough work to fill the chip, shorter otherwise.
+// OZL_MSM_WAVES=1 (experiment, measured and left off): pick the slice length that fills whole "waves" of resident
+// threads (2^20 points x 16 windows on 12 limbs = 2.31 waves of 128-entry slices -> three waves of 104).  It does not
+// pay: the kernel is bound by the multiplier pipe, not by latency, so the warps left in a partial last wave simply run
+// faster -- 2^20: 5.66 -> 5.92 ms (more slices, more flushes), 2^22: 18.45 -> 17.84 ms, 2^24 and Groth16 unchanged.
+inline uint32_t slice_len(uint64_t entries, uint32_t resident) {
+  static const int kForceL = []() { const char* e = getenv("OZL_MSM_L"); return e ? atoi(e) : 0; }();
+  if (kForceL >= 8) return (uint32_t)kForceL & ~7u;
+  static const bool kWaves = []() { const char* e = getenv("OZL_MSM_WAVES"); return e && e[0] == '1'; }();
+  uint64_t L;
+  if (kWaves) {
+    uint64_t waves = (entries + (uint64_t)128 * resident - 1) / ((uint64_t)128 * resident);
+    if (waves < 1) waves = 1;
+    L = (entries + waves * resident - 1) / (waves * resident);
+    L = (L + 7) & ~(uint64_t)7;   // multiple of 8 entries: slices start 32-byte aligned (TMA needs 16)
+  } else {
+    L = (entries / ((uint64_t)148 * 384)) & ~(uint64_t)7;
+  }
   if (L > 128) L = 128;
   if (L < 8) L = 8;
-  static const int kForceL = []() { const char* e = getenv("OZL_MSM_L"); return e ? atoi(e) : 0; }();
-  if (kForceL >= 8) L = (uint64_t)kForceL;
-  return (uint32_t)L & ~7u;   // multiple of 8 entries: slices start 32-byte aligned (TMA needs 16)
+  return (uint32_t)L;
 }
 
 // Window width: minimise field multiplications  n*W*10 (mixed adds) + 2*Wc*B*95 + (n*W/128)*45
@@ -223,7 +252,7 @@ inline MsmPlan make_plan(int curve, size_t n, int forced_c, int fixed_Wc = 0, in
   p.B = 1u << (p.c - 1);
   p.Wc = fixed_Wc ? fixed_Wc : p.W;
   p.NB = (uint32_t)p.Wc * p.B;
-  p.L = slice_len((uint64_t)n * p.W);   // 128 entries per accumulate thread when there is enough work to fill the chip, shorter otherwise
+  p.L = slice_len((uint64_t)n * p.W, resident_acc_threads(coord_u32(curve)));   // 128 entries per accumulate thread when there is enough work to fill the chip, shorter otherwise
   uint32_t chunk = p.B / 4096;
   if (chunk < 4) chunk = 4;
   if (chunk > 16) chunk = 16;
@@ -352,6 +381,30 @@ int run_pair_levels(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
 // (the copy is issued HERE, batch by batch, so that it also overlaps when the caller's memory is
 // pageable and cudaMemcpyAsync blocks the host thread).
 static constexpr int MSM_MAX_BATCHES = 8;
+static constexpr int MSM_MAX_INTERVALS = 16;   // accumulation launches of one batch of the pipelined MSM
+// ws.misc words: [0] slice counter of a whole-array accumulation, [8] input-error flags,
+// [16 + j * MSM_MAX_INTERVALS + k] slice counter of interval k of batch j
+static constexpr size_t MISC_BYTES = (16 + (size_t)MSM_MAX_BATCHES * MSM_MAX_INTERVALS) * 4;
+
+// Pipelined MSM: streams and events of a workspace, created on first use.
+inline int ensure_pipe(ozl_ctx* ctx, MsmWorkspace& ws) {
+  if (ws.acc_stream[0]) return OZL_OK;
+  int lo = 0, hi = 0;
+  CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = greatest priority
+  static const int kPrio = []() { const char* e = getenv("OZL_PIPE_PRIO"); return e ? atoi(e) : 1; }();   // 0: all streams at the default priority
+  // The SORT stream gets the greatest priority and its co-running launches a grid that needs only the registers the
+  // accumulation leaves free, so they are placed at once; the accumulation streams keep the default (lowest) priority,
+  // so the pending CTAs of the next interval never hold the sort back (measured the other way round: a pending
+  // high-priority accumulation launch starved the scatter of the following interval for 60 ms).
+  CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ws.sort_stream, cudaStreamNonBlocking, kPrio ? hi : lo));
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&ws.ev_sort_ready, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ws.acc_stream[i], cudaStreamNonBlocking, lo));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ws.ev_acc_done[i], cudaEventDisableTiming));
+  }
+  for (int k = 0; k < MSM_MAX_INTERVALS; k++) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ws.ev_interval[k], cudaEventDisableTiming));
+  return OZL_OK;
+}
 
 struct MsmBatches {
   int J = 1;
@@ -384,7 +437,7 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
   uint32_t Lj[MSM_MAX_BATCHES], heavy[MSM_MAX_BATCHES];
   for (int j = 0; j < J; j++) {
     max_nj = std::max(max_nj, mb.count[j]);
-    Lj[j] = J == 1 ? p.L : slice_len((uint64_t)mb.count[j] * p.W);
+    Lj[j] = J == 1 ? p.L : slice_len((uint64_t)mb.count[j] * p.W, resident_acc_threads(F::N, ctx->sm_count));
   }
   int r;
   if ((r = ensure(ctx, ws.counts, (size_t)p.NB * 4))) return r;
@@ -397,7 +450,7 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
   }
   if ((r = ensure(ctx, ws.chunk_out, ((size_t)p.Wc * p.K + (size_t)p.Wc * 64) * XY * 4))) return r;
   if ((r = ensure(ctx, ws.window_out, (size_t)p.Wc * XY * 4))) return r;
-  if ((r = ensure(ctx, ws.misc, 64))) return r;
+  if ((r = ensure(ctx, ws.misc, MISC_BYTES))) return r;
   uint32_t* lvl_off = nullptr;
   if (T) {
     if ((r = ensure(ctx, ws.lvl_off, (size_t)T * ((size_t)p.NB + 1) * 4))) return r;
@@ -413,7 +466,8 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
   const int grid_io = ctx->sm_count * 8;
   FoldRegions regions;
   regions.J = J;
-  CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 64, st));
+  bool pipe_pending = false;   // accumulation launches outstanding on the side streams
+  CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, MISC_BYTES, st));
 
   for (int j = 0; j < J; j++) {
     const size_t first = mb.first[j], nj = mb.count[j];
@@ -440,25 +494,166 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
       if ((r = run_scan(ctx, ws, st, counts, p.NB, lvl_off + (size_t)(l - 1) * (p.NB + 1), ScanCeilDiv{1u << l}))) return r;
     STAGE_END(ctx);
 
-    STAGE_ON(ctx, "scatter", st);
+    // ---- scatter + accumulate --------------------------------------------------------------------------------
+    // The counting sort runs bucket-set-major, then one bucket RANGE of 2^18 buckets (8 MB of open 32-byte sectors)
+    // at a time so that a bucket's region is completed while its sectors are still in L2 (measured at 2^26, c = 22,
+    // 2^21 buckets: 34.2 / 27.9 / 26.9 / 23.3 ms with 1 / 2 / 4 / 8 ranges, re-reading the digits included), then the
+    // windows that share the set.  After group (set s, range q) the bucket interval [s B + lo_q, s B + hi_q) of the
+    // sorted array is final, and the intervals complete in increasing order.
+    //
+    // PIPELINED (large MSMs on the G1 curves): the accumulation of a finished interval starts at once, on one of two
+    // high-priority side streams, while this stream goes on scattering the next interval.  The interval kernels are
+    // one warp per CTA and capped at 160 (120) registers, which leaves 4096 registers per SM: the four scatter warps
+    // per SM that fit there are latency-bound on L2 atomics and take next to nothing from the multiplier pipe the
+    // accumulation is bound by.  Alternating streams let interval k + 1 take over SMs warp by warp as interval k runs
+    // out of slices.  Only the first interval's sort stays exposed.
+    static const int kForceParts = []() { const char* e = getenv("OZL_MSM_SCATTER_PARTS"); return e ? atoi(e) : 0; }();
+    // OZL_MSM_PIPE: 0 = off (DEFAULT: measured slower on B200, see below), -1 = on from ~2^24 points, k > 0 = on at any size with at most k intervals
+    static const int kPipe = []() { const char* e = getenv("OZL_MSM_PIPE"); return e ? atoi(e) : 0; }();
+    static const int kPipeRegs = []() { const char* e = getenv("OZL_PIPE_REGS"); return e ? atoi(e) : 0; }();   // interval kernels capped 0 / 16 / 32 registers lower
+    static const int kScatterU = []() { const char* e = getenv("OZL_SCATTER_U"); return e ? atoi(e) : 1; }();
+    static const int kPipeStreams = []() { const char* e = getenv("OZL_PIPE_STREAMS"); return e ? atoi(e) : 1; }();
+    static const int kPipeLayout = []() { const char* e = getenv("OZL_PIPE_LAYOUT"); return e ? atoi(e) : 1; }();   // 1 = doubling interval lengths, 0 = equal
+    static const int kPipeSpread = []() { const char* e = getenv("OZL_PIPE_SPREAD"); return e ? atoi(e) : 1; }();   // 1 = one wide scatter CTA per SM
+    static const int kPipeScatterCtas = []() { const char* e = getenv("OZL_PIPE_SCATTER_CTAS"); return e ? std::max(1, atoi(e)) : 4; }();   // co-resident 128-thread scatter CTAs per SM
+    static const int kScatterGrid = []() { const char* e = getenv("OZL_SCATTER_GRID"); return e ? atoi(e) : 0; }();   // diagnostic: 128-thread CTAs per SM
+    uint32_t parts = kForceParts > 0 ? (uint32_t)kForceParts : std::min<uint32_t>(16u, std::max<uint32_t>(1u, p.B >> 18));
+    if (parts > p.B) parts = p.B;
+    const uint32_t span = (p.B + parts - 1) / parts;
+    const uint32_t groups = (uint32_t)p.Wc * parts;
+    static const bool use_tma = []() { const char* e = getenv("OZL_ACC_TMA"); return !(e && e[0] == '0'); }();
+    static const int acc_env = []() { const char* e = getenv("OZL_ACC_MODE"); return e ? atoi(e) : -1; }();
+    const int acc_mode = acc_env >= 0 ? acc_env : (F::N == 8 ? 6 : 5);   // BN254 G1 (8 limbs, ~45 KB inlined) is 4 % faster inlined + fused
+    // intervals = accumulation launches of this batch: enough slices per launch for several full waves of the chip
+    uint32_t intervals = 1;
+    if (F::N <= 12 && !T && use_tma && acc_env < 0 && kPipe != 0 && groups > 1 && nj) {
+      const uint64_t slices = (uint64_t)nj * p.W / Lj[j];
+      const uint64_t resident = (uint64_t)ctx->sm_count * AccPipe<F>::WARPS_PER_SM * 32;
+      intervals = std::min<uint32_t>(groups, kPipe > 0 ? (uint32_t)kPipe : 8u);
+      if (kPipe < 0) intervals = (uint32_t)std::min<uint64_t>(intervals, slices / (4 * resident));   // OZL_MSM_PIPE=k forces it at any size (tests)
+      if (intervals > MSM_MAX_INTERVALS) intervals = MSM_MAX_INTERVALS;
+      if (intervals < 2) intervals = 1;
+    }
+    const bool pipe = intervals > 1;
+    if (pipe && (r = ensure_pipe(ctx, ws))) return r;
+    const cudaStream_t ss = pipe ? ws.sort_stream : st;   // stream of the scatter launches
+    // interval k ends after group gend[k]: the first interval is ONE group (its sort is the exposed one)
+    uint32_t gend[MSM_MAX_INTERVALS];
+    if (pipe && kPipeLayout == 1) {
+      // doubling: 1, 1, 2, 4, ... groups per interval.  Every launch boundary costs a drain bubble (the last slices of
+      // a launch finish up to one slice = 2.4 ms apart), and a sort that co-runs at a quarter of its speed is
+      // through long before the accumulation is, so late intervals can be long.
+      uint32_t k = 0, e = 1;
+      while (k + 1 < std::min<uint32_t>(intervals, MSM_MAX_INTERVALS) && e < groups) { gend[k++] = e; e = std::min(groups, e * 2); }
+      gend[k++] = groups;
+      intervals = k;
+    } else {
+      for (uint32_t k = 0; k < intervals; k++)
+        gend[k] = intervals == 1 ? groups : (k == 0 ? 1u : 1u + (uint32_t)(((uint64_t)(groups - 1) * k) / (intervals - 1)));
+    }
+    uint32_t* partials_j = partials;
+    // OZL_PIPE_TRACE=1 (diagnostic): timeline of the scatter groups and the interval launches, printed to stderr
+    static const bool kTrace = []() { const char* e = getenv("OZL_PIPE_TRACE"); return e && e[0] == '1'; }();
+    std::vector<cudaEvent_t> tr_g, tr_a0, tr_a1;
+    cudaEvent_t tr_t0 = nullptr;
+    auto tr_rec = [&](std::vector<cudaEvent_t>& v, cudaStream_t q) {
+      cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, q); v.push_back(e);
+    };
+    if (kTrace && pipe) { cudaEventCreate(&tr_t0); cudaEventRecord(tr_t0, st); }   // before the sort stream's first launch
+    auto launch_interval = [&](uint32_t k, uint32_t g_lo, uint32_t g_hi) -> int {
+      cudaStream_t sa = ws.acc_stream[kPipeStreams == 1 ? 0 : (k & 1)];
+      CUDA_TRY(ctx, cudaEventRecord(ws.ev_interval[k], ss));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(sa, ws.ev_interval[k], 0));
+      if (k < 2 && ws.accumulate_gate) CUDA_TRY(ctx, cudaStreamWaitEvent(sa, ws.accumulate_gate, 0));
+      if (k == 0) STAGE_ON(ctx, "accumulate", sa);
+      if (kTrace) tr_rec(tr_a0, sa);
+      uint32_t* counter = work_counter + 16 + (size_t)j * MSM_MAX_INTERVALS + k;
+      const int grid = ctx->sm_count * AccPipe<F>::WARPS_PER_SM;
+      if constexpr (F::N <= 12) {
+        constexpr int R0 = AccPipe<F>::MAXREG;
+        constexpr int M = F::N <= 8 ? 6 : 5;   // shipped product variant of the field (see acc_mode above)
+        // the SM must be in its largest shared-memory configuration for the pinned scatter CTA to fit beside these warps
+        static const bool carve_set = []() {
+          cudaFuncSetAttribute(k_accumulate_tma_piece<F, M, R0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          cudaFuncSetAttribute(k_accumulate_tma_piece<F, M, R0 - 16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          cudaFuncSetAttribute(k_accumulate_tma_piece<F, M, R0 - 32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          return true;
+        }();
+        (void)carve_set;
+        if (kPipeRegs == 2) k_accumulate_tma_piece<F, M, R0 - 32><<<grid, 32, 0, sa>>>(b.d_pts, sorted, offsets, p.NB, Lj[j], counter, partials_j, g_lo, g_hi);
+        else if (kPipeRegs == 1) k_accumulate_tma_piece<F, M, R0 - 16><<<grid, 32, 0, sa>>>(b.d_pts, sorted, offsets, p.NB, Lj[j], counter, partials_j, g_lo, g_hi);
+        else k_accumulate_tma_piece<F, M, R0><<<grid, 32, 0, sa>>>(b.d_pts, sorted, offsets, p.NB, Lj[j], counter, partials_j, g_lo, g_hi);
+      } else {
+        (void)counter; (void)grid; (void)g_lo; (void)g_hi;
+        ctx->last_error = "msm: interval launches exist for the G1 curves only";
+        return OZL_ERR_ARG;
+      }
+      LAUNCH_CHECK(ctx);
+      if (kTrace) tr_rec(tr_a1, sa);
+      return OZL_OK;
+    };
+
+    if (pipe_pending) {   // `sorted` is about to be overwritten: the previous batch's accumulations must be through
+      CUDA_TRY(ctx, cudaStreamWaitEvent(st, ws.ev_acc_done[0], 0));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(st, ws.ev_acc_done[1], 0));
+    }
+    if (pipe) {
+      CUDA_TRY(ctx, cudaEventRecord(ws.ev_sort_ready, st));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ss, ws.ev_sort_ready, 0));
+    }
+    STAGE_ON(ctx, "scatter", ss);
     {
-      // bucket ranges of 2^18 buckets per pass (8 MB of open sectors), range-major so a bucket's region
-      // is completed while its sectors are still in L2.  Measured at 2^26, c = 22 (2^21 buckets):
-      // 34.2 / 27.9 / 26.9 / 23.3 ms with 1 / 2 / 4 / 8 ranges, re-reading the digits included.
-      static const int kForceParts = []() { const char* e = getenv("OZL_MSM_SCATTER_PARTS"); return e ? atoi(e) : 0; }();
-      uint32_t parts = kForceParts > 0 ? (uint32_t)kForceParts : std::min<uint32_t>(16u, std::max<uint32_t>(1u, p.B >> 18));
-      if (parts > p.B) parts = p.B;
-      const uint32_t span = (p.B + parts - 1) / parts;
-      for (uint32_t q = 0; q < parts && nj; q++) {
+      uint32_t k = 0, g_lo = 0;
+      for (uint32_t grp = 0; grp < groups && nj; grp++) {
+        const uint32_t s_ = grp / parts, q = grp % parts;
         const uint32_t lo = q * span, hi = std::min<uint32_t>(p.B, lo + span);
-        for (int w = 0; w < p.W; w++) {
-          k_scatter_window<<<grid_io, 256, 0, st>>>(digits + (size_t)w * nj, (uint32_t)nj, (uint32_t)(w % p.Wc) * p.B,
-                                                   (uint32_t)((size_t)(w / p.Wc) * b.n + first), offsets, counts, sorted, lo, hi);
+        for (int w = (int)s_; w < p.W; w += p.Wc) {
+          const uint32_t* dw = digits + (size_t)w * nj;
+          const uint32_t idx0 = (uint32_t)((size_t)(w / p.Wc) * b.n + first);
+          if (pipe || kScatterGrid > 0) {
+            // 128-thread CTAs.  The first interval's groups run alone and take the whole chip; the others run under an
+            // accumulation launch, in a grid of exactly the CTAs that fit into the registers it leaves free.
+            if (pipe && k > 0 && kPipeSpread && kScatterGrid <= 0) {
+              // ONE CTA of 128 x kPipeScatterCtas threads per SM, pinned there by a dynamic shared memory request that
+              // a second copy cannot meet (the block scheduler otherwise packs sixteen small CTAs onto a quarter of the
+              // SMs and the accumulation loses those SMs outright: measured zero-sum) but that fits beside the twelve
+              // accumulation warps (12 x (8200 + 1024) + 118 KB + 1024 <= 228 KB).
+              constexpr size_t kPin = 115968;   // two copies (+ 1 KB each) exceed the SM's 228 KB; one fits beside the accumulation's 12 x 9.25 KB
+              static const bool attr_set = []() {
+                cudaFuncSetAttribute(k_scatter_window<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPin);
+                cudaFuncSetAttribute(k_scatter_window<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPin);
+                cudaFuncSetAttribute(k_scatter_window<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k_scatter_window<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                return true;
+              }();
+              (void)attr_set;
+              const int threads = 128 * std::min(4, kPipeScatterCtas);
+              if (kScatterU == 2) k_scatter_window<2><<<ctx->sm_count, threads, kPin, ss>>>(dw, (uint32_t)nj, s_ * p.B, idx0, offsets, counts, sorted, lo, hi);
+              else k_scatter_window<1><<<ctx->sm_count, threads, kPin, ss>>>(dw, (uint32_t)nj, s_ * p.B, idx0, offsets, counts, sorted, lo, hi);
+              LAUNCH_CHECK(ctx);
+              continue;
+            }
+            const int g128 = kScatterGrid > 0 ? ctx->sm_count * kScatterGrid : (k == 0 ? grid_io * 2 : ctx->sm_count * kPipeScatterCtas);
+            if (kScatterU == 2) k_scatter_window<2><<<g128, 128, 0, ss>>>(dw, (uint32_t)nj, s_ * p.B, idx0, offsets, counts, sorted, lo, hi);
+            else k_scatter_window<1><<<g128, 128, 0, ss>>>(dw, (uint32_t)nj, s_ * p.B, idx0, offsets, counts, sorted, lo, hi);
+          } else {
+            k_scatter_window<1><<<grid_io, 256, 0, ss>>>(dw, (uint32_t)nj, s_ * p.B, idx0, offsets, counts, sorted, lo, hi);
+          }
           LAUNCH_CHECK(ctx);
+        }
+        if (kTrace && pipe) tr_rec(tr_g, ss);
+        if (pipe && grp + 1 == gend[k]) {
+          const uint32_t g_hi = grp + 1 == groups ? p.NB : s_ * p.B + hi;
+          if (k == 0) STAGE_END(ctx);   // the "scatter" stage times the exposed part: the first interval's sort
+          if ((r = launch_interval(k, g_lo, g_hi))) return r;
+          g_lo = g_hi;
+          k++;
         }
       }
     }
-    STAGE_END(ctx);
+    if (!pipe) STAGE_END(ctx);
+    // the next batch's digit extraction overwrites `digits` and `counts`: the main stream waits for the last scatter
+    if (pipe) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ws.ev_interval[intervals - 1], 0));
 
     const uint32_t* acc_offsets = offsets;   // offsets of the lists the XYZZ accumulation walks
     uint32_t acc_L = Lj[j];
@@ -467,40 +662,77 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
       if ((r = run_pair_levels<F>(ctx, ws, st, b, p, bc, T, nj, sorted, offsets, lvl_off))) return r;
       STAGE_END(ctx);
       acc_offsets = lvl_off + (size_t)(T - 1) * (p.NB + 1);
-      acc_L = slice_len(((uint64_t)nj * p.W) >> T);
+      acc_L = slice_len(((uint64_t)nj * p.W) >> T, resident_acc_threads(F::N, ctx->sm_count));
       const size_t slots = (size_t)p.NB + ((((size_t)nj * p.W) >> T) + p.NB) / acc_L + 2;
       if ((r = ensure(ctx, ws.partials[j], slots * XY * 4))) return r;
       partials = (uint32_t*)ws.partials[j].p;
     }
 
+    if (pipe) {
+      // the stage ends when both side streams are through; the main stream only joins them where it has to
+      // (before the next batch's scatter, above, and before the bucket reduction, below)
+      for (int i = 0; i < 2; i++) CUDA_TRY(ctx, cudaEventRecord(ws.ev_acc_done[i], ws.acc_stream[i]));
+      if (ctx->timing) {
+        const int last_i = kPipeStreams == 1 ? 0 : (int)((intervals - 1) & 1);
+        cudaStream_t last = ws.acc_stream[last_i];
+        CUDA_TRY(ctx, cudaStreamWaitEvent(last, ws.ev_acc_done[last_i ^ 1], 0));
+        nvtxRangePop();
+        for (auto it = ctx->stages.rbegin(); it != ctx->stages.rend(); ++it)
+          if (it->name == "accumulate") { CUDA_TRY(ctx, cudaEventRecord(it->e1, last)); break; }
+        CUDA_TRY(ctx, cudaEventRecord(ws.ev_acc_done[last_i], last));
+      } else {
+        nvtxRangePop();
+      }
+      pipe_pending = true;
+      if (kTrace) {
+        cudaStreamSynchronize(ws.acc_stream[0]);
+        cudaStreamSynchronize(ws.acc_stream[1]);
+        cudaStreamSynchronize(st);
+        auto at = [&](cudaEvent_t e) { float ms = 0; cudaEventElapsedTime(&ms, tr_t0, e); return ms; };
+        fprintf(stderr, "[pipe trace] batch %d: %u groups, %u intervals, L %u\n  scatter group ends:", j, groups, intervals, Lj[j]);
+        for (auto e : tr_g) fprintf(stderr, " %.2f", at(e));
+        fprintf(stderr, "\n  interval [ready, end]:");
+        for (size_t i = 0; i < tr_a0.size(); i++) fprintf(stderr, " [%.2f, %.2f]", at(tr_a0[i]), at(tr_a1[i]));
+        fprintf(stderr, "\n");
+        for (auto e : tr_g) cudaEventDestroy(e);
+        for (auto e : tr_a0) cudaEventDestroy(e);
+        for (auto e : tr_a1) cudaEventDestroy(e);
+        cudaEventDestroy(tr_t0);
+      }
+    } else {
     if (ws.accumulate_gate) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ws.accumulate_gate, 0));
     STAGE_ON(ctx, "accumulate", st);
     if (T) {
       k_accumulate<F, true><<<ctx->sm_count * 4, 128, 0, st>>>((const uint32_t*)ws.lvl_pts.p, nullptr, acc_offsets, p.NB, acc_L, work_counter, partials);
     } else {
+      // grid: persistent (one CTA per resident slot, warps loop until the counter runs out) or, for a workspace that
+      // yields, one CTA per four 32-slice batches, each warp taking exactly one
+      static const int kYield = []() { const char* e = getenv("OZL_ACC_YIELD"); return e ? atoi(e) : -1; }();   // 0 / 1 override the workspace flag
+      const bool yield = kYield >= 0 ? kYield != 0 : ws.yield_ctas;
+      const uint64_t acc_slices = ((uint64_t)nj * p.W + acc_L - 1) / acc_L + 1;
+      const uint32_t acc_grid = yield ? (uint32_t)std::max<uint64_t>(1, ((acc_slices + 31) / 32 + 3) / 4) : (uint32_t)ctx->sm_count * 4;
+      const uint32_t acc_batches = yield ? 1u : 0xffffffffu;
       // TMA-staged index stream by default; OZL_ACC_TMA=0 selects the plain global-load variant
-      static const bool use_tma = []() { const char* e = getenv("OZL_ACC_TMA"); return !(e && e[0] == '0'); }();
       // Field products of the hot loop (XYZZ::add_mixed_calls): 0 = all inlined, 1 = out-of-line mul (operands by
       // value), 2 = out-of-line paired mul, 3 = 1 + dedicated squaring, 4 = 3 with Karatsuba products, 5 = 3 with
       // y3 = r (q - x3) - y p3 as one fused dual product (single reduction), 6 = inlined + fused y3.
       // Measured on B200, accumulate stage at 2^26 BLS12-381 G1: 296.9 / 282.9 / 284.3 / 277.5 / 310.4 / 260.4 ms
       // for 0 .. 5: the inlined body (~100 KB of SASS) misses the instruction cache (ncu: icc hit rate 83.5 % ->
       // 99.998 %, fmaheavy 85.3 % -> 92.9 %), and the fused y3 saves N^2 of the 20 N^2 wide multiplies of an addition.
-      static const int acc_env = []() { const char* e = getenv("OZL_ACC_MODE"); return e ? atoi(e) : -1; }();
-      const int acc_mode = acc_env >= 0 ? acc_env : (F::N == 8 ? 6 : 5);   // BN254 G1 (8 limbs, ~45 KB inlined) is 4 % faster inlined + fused
       if (use_tma && acc_mode == 1) k_accumulate_tma<F, 1><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 2) k_accumulate_tma<F, 2><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 3) k_accumulate_tma<F, 3><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 13 && F::N == 12) k_accumulate_tma<F, 3, (F::N == 12 ? 4 : 2)><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);   // experiment: 4 CTAs per SM at 128 registers
-      else if (use_tma && acc_mode == 6 && F::N <= 12) k_accumulate_tma<F, (F::N <= 12 ? 6 : 0)><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else if (use_tma && acc_mode == 6 && F::N <= 12) k_accumulate_tma<F, (F::N <= 12 ? 6 : 0)><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);
       else if (use_tma && acc_mode == 7) k_accumulate_tma<F, 7><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
-      else if (use_tma && acc_mode == 5) k_accumulate_tma<F, 5><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
+      else if (use_tma && acc_mode == 5) k_accumulate_tma<F, 5><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);
       else if (use_tma && acc_mode == 4) k_accumulate_tma<F, 4><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma) k_accumulate_tma<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else k_accumulate<F><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
     }
     LAUNCH_CHECK(ctx);
     STAGE_END(ctx);
+    }
 
     // "heavy" = far more slice partials than the average bucket has (skew), not merely many
     const uint32_t acc_entries = (uint32_t)std::min<uint64_t>(T ? ((((uint64_t)nj * p.W) >> T) + p.NB) : (uint64_t)nj * p.W, 0xffffffffull);
@@ -511,6 +743,10 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
     regions.heavy_t[j] = heavy[j];
   }
 
+  if (pipe_pending) {
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ws.ev_acc_done[0], 0));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ws.ev_acc_done[1], 0));
+  }
   STAGE_ON(ctx, "bucket_reduce", st);
   if (n) {
     // heavy-bucket collapse: 3 passes cover 2^30 partials per bucket; no-ops when nothing is heavy
@@ -665,6 +901,14 @@ inline void free_workspace(MsmWorkspace& ws) {
                     &ws.partials[0], &ws.partials[1], &ws.partials[2], &ws.partials[3], &ws.partials[4], &ws.partials[5], &ws.partials[6], &ws.partials[7]};
   for (DevBuf* b : bufs)
     if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+  for (int i = 0; i < 2; i++) {
+    if (ws.acc_stream[i]) { cudaStreamDestroy(ws.acc_stream[i]); ws.acc_stream[i] = nullptr; }
+    if (ws.ev_acc_done[i]) { cudaEventDestroy(ws.ev_acc_done[i]); ws.ev_acc_done[i] = nullptr; }
+  }
+  for (auto& e : ws.ev_interval)
+    if (e) { cudaEventDestroy(e); e = nullptr; }
+  if (ws.sort_stream) { cudaStreamDestroy(ws.sort_stream); ws.sort_stream = nullptr; }
+  if (ws.ev_sort_ready) { cudaEventDestroy(ws.ev_sort_ready); ws.ev_sort_ready = nullptr; }
 }
 
 }  // namespace ozl_rt
