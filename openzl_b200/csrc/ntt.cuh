@@ -167,7 +167,9 @@ static constexpr int NTT_TILE_THREADS = 256;
 static constexpr int NTT_TILE_SMEM_HALVES = NTT_TILE_ELEMS + 512;
 static constexpr int NTT_TILE_SMEM_BYTES = 2 * NTT_TILE_SMEM_HALVES * 16;
 
-template <class P>
+// PAIRED: the four products of a stage go through two calls of the paired out-of-line multiplier (two independent
+// carry chains interleaved in one body) instead of four inlined bodies.
+template <class P, bool PAIRED = false>
 __global__ void __launch_bounds__(NTT_TILE_THREADS, 2)
 k_ntt_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ tw, int log_n, int s, int R,
            int pre, int post, int last, const uint32_t* __restrict__ glo, const uint32_t* __restrict__ ghi,
@@ -237,6 +239,26 @@ k_ntt_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ui
       }
 #pragma unroll 1
       for (int r = 0; r < 3; r++) {
+        if (PAIRED) {
+          F w[4], d[4];
+          bool any = false;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const uint32_t e = exponent(r, i);
+            w[i] = F::load(tw + (size_t)e * F::N);     // tw[0] = 1
+            any |= e != 0;
+            const F a = x[i], b = x[i + 4];
+            x[i] = a + b;
+            d[i] = a - b;
+          }
+          if (any) {
+            const typename F::Pair p0 = F::mul2_ni(d[0], w[0], d[1], w[1]);
+            const typename F::Pair p1 = F::mul2_ni(d[2], w[2], d[3], w[3]);
+            x[4] = p0.a; x[5] = p0.b; x[6] = p1.a; x[7] = p1.b;
+          } else {
+            x[4] = d[0]; x[5] = d[1]; x[6] = d[2]; x[7] = d[3];
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const uint32_t e = exponent(r, i);
@@ -248,6 +270,7 @@ k_ntt_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ui
             const F w = F::load(tw + (size_t)e * F::N);
             x[i + 4] = (a - b) * w;
           }
+        }
         }
         // rotate the index bits left: b2 b1 b0 -> b1 b0 b2
         const F t1 = x[1], t2 = x[2], t3 = x[3], t4 = x[4], t5 = x[5], t6 = x[6];
@@ -348,7 +371,9 @@ int ntt_run(cudaStream_t st, NttWorkspace& ws, int field_id, uint32_t* d_data, u
     }
   }
   // per device, so not cached in a static: a process may hold contexts on several GPUs
-  if (cudaFuncSetAttribute(k_ntt_tile<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TILE_SMEM_BYTES) != cudaSuccess) return -3;
+  static const bool kPaired = []() { const char* e = getenv("OZL_NTT_PAIRED"); return e && e[0] == '1'; }();
+  if (cudaFuncSetAttribute(k_ntt_tile<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TILE_SMEM_BYTES) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_ntt_tile<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TILE_SMEM_BYTES) != cudaSuccess) return -3;
   uint32_t* scratch = (uint32_t*)ws.scratch;
   int s = 0;
   for (int pi = 0; pi < np; pi++) {
@@ -361,7 +386,8 @@ int ntt_run(cudaStream_t st, NttWorkspace& ws, int field_id, uint32_t* d_data, u
     if (lastp && inverse) post = coset ? 2 : 1;
     if (tiled[pi]) {
       const uint32_t blocks = (uint32_t)(n / NTT_TILE_ELEMS);
-      k_ntt_tile<P><<<blocks, NTT_TILE_THREADS, NTT_TILE_SMEM_BYTES, st>>>(src, dst, tw, log_n, s, R, pre, post, lastp, glo, ghi, &consts->size_inv);
+      if (kPaired) k_ntt_tile<P, true><<<blocks, NTT_TILE_THREADS, NTT_TILE_SMEM_BYTES, st>>>(src, dst, tw, log_n, s, R, pre, post, lastp, glo, ghi, &consts->size_inv);
+      else k_ntt_tile<P, false><<<blocks, NTT_TILE_THREADS, NTT_TILE_SMEM_BYTES, st>>>(src, dst, tw, log_n, s, R, pre, post, lastp, glo, ghi, &consts->size_inv);
     } else {
       const uint32_t threads = (uint32_t)(n >> R);
       static const int kBlock = []() { const char* e = getenv("OZL_NTT_BLOCK"); int v = e ? atoi(e) : 128; return (v == 32 || v == 64 || v == 128) ? v : 128; }();

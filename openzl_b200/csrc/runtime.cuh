@@ -438,6 +438,9 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
   for (int j = 0; j < J; j++) {
     max_nj = std::max(max_nj, mb.count[j]);
     Lj[j] = J == 1 ? p.L : slice_len((uint64_t)mb.count[j] * p.W, resident_acc_threads(F::N, ctx->sm_count));
+    // a yielding workspace hands its SMs back every slice: 64-entry slices halve that interval (0.8 ms on G1, 1.1 ms on
+    // G2 at the Groth16 sizes) for twice the slice partials -- measured 22.07 -> 21.79 ms per proof
+    if (ws.yield_ctas && Lj[j] > 64) Lj[j] = 64;
   }
   int r;
   if ((r = ensure(ctx, ws.counts, (size_t)p.NB * 4))) return r;

@@ -202,6 +202,39 @@ def test_prove_2p16_constraints_matches_oracle_and_verifies(ctx):
         pk.free()
 
 
+def test_prove_baseline_size_2p20_constraints_verifies(ctx):
+    """BASELINE config 4 itself: 3013 Poseidon links = 1,048,524 constraints (domain 2^20).  The proof of the device
+    prover passes the pairing equation in the product's host verifier, a wrong public input is rejected, the proof
+    is reproducible (two calls, same randomness, same bytes -- the prover's four streams race on nothing), and A and
+    B equal [alpha + <z, a> + r delta]G1 / [beta + <z, b> + s delta]G2 computed from the setup scalars."""
+    links = 3013
+    ch = PoseidonChain(links)
+    r1 = ch.r1cs()
+    assert r1.n_constraints == 1048524
+    z = ch.assignment(99, 1234)
+    td = _trapdoor(20)
+    pk, vk = Groth16.compile(ctx, "bn254", r1, td, keep_queries=True, precompute=32)
+    try:
+        assert pk.domain_size == 1 << 20
+        rnd = random.Random(20)
+        r, s = rnd.randrange(P), rnd.randrange(P)
+        z_m = ints_to_limbs(z, P, mont=True)
+        proof = Groth16.prove_with_randomness(pk, z_m, r, s)
+        again = Groth16.prove_with_randomness(pk, z_m, r, s)
+        assert (proof.a == again.a).all() and (proof.b == again.b).all() and (proof.c == again.c).all()
+        qa, qb = pk.queries["a"], pk.queries["b"]
+        m = r1.n_vars
+        A = (td.alpha + sum(z[j] * qa[j] for j in range(m)) + r * td.delta) % P
+        B = (td.beta + sum(z[j] * qb[j] for j in range(m)) + s * td.delta) % P
+        for name, k, got in (("bn254_g1", A, proof.a), ("bn254_g2", B, proof.b)):
+            exp, exp_inf = cbind.to_affine(name, cbind.gen_mul(name, k))
+            assert not exp_inf and (got == exp).all(), name
+        assert Groth16.verify(vk, [z[1]], proof)
+        assert not Groth16.verify(vk, [(z[1] + 1) % P], proof)
+    finally:
+        pk.free()
+
+
 def test_proving_key_bytes_to_device_round_trip(ctx):
     """Row f-3 end to end (`ProvingContext::{encode, decode}`, groth16.rs:142-179): the device key is
     encoded as ark's unchecked uncompressed ProvingKey bytes, decoded, re-uploaded through
