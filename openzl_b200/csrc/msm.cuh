@@ -436,7 +436,9 @@ __device__ __forceinline__ void accumulate_tma_body(const uint32_t* __restrict__
 // CTA retires -- unbounded for a persistent grid of resident CTAs (a lone MSM), 1 for a grid of one CTA per four
 // batches, which hands the SM back to the block scheduler every slice (~2 ms) so that kernels of OTHER streams get
 // in by priority instead of waiting for this launch to run dry (Groth16 prover: five MSMs on four streams).
-template <class F, int MODE = 0, int MINB = (F::N <= 8 ? 4 : (F::N <= 12 ? 3 : 2))>
+// BN254 G2 (16 limbs per coordinate) runs THREE CTAs per SM at 168 registers (324 B of spills) rather than two at 255:
+// accumulate 10.28 -> 9.49 ms at 2^20 x 15 windows; BLS12-381 G2 (24 limbs) loses at 168 (23.3 -> 31.0 ms) and keeps two.
+template <class F, int MODE = 0, int MINB = (F::N <= 8 ? 4 : (F::N <= 16 ? 3 : 2))>
 __global__ void __launch_bounds__(128, MINB)
 k_accumulate_tma(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
                  uint32_t NB, uint32_t L, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ partials,

@@ -197,9 +197,9 @@ inline int coord_u32(int curve) {
 }
 inline int scalar_bits(int curve) { return (curve == OZL_BLS12_381_G1 || curve == OZL_BLS12_381_G2) ? 255 : 254; }
 
-// Accumulation threads resident on the chip: 4 / 3 / 2 CTAs of 128 threads per SM for 8 / 12 / more limbs per coordinate.
+// Accumulation threads resident on the chip: 4 / 3 / 3 / 2 CTAs of 128 threads per SM for 8 / 12 / 16 / 24 limbs per coordinate.
 inline uint32_t resident_acc_threads(int limbs_u32, int sm_count = 148) {
-  return (uint32_t)sm_count * 128u * (limbs_u32 <= 8 ? 4u : (limbs_u32 <= 12 ? 3u : 2u));
+  return (uint32_t)sm_count * 128u * (limbs_u32 <= 8 ? 4u : (limbs_u32 <= 16 ? 3u : 2u));
 }
 // Entries per accumulation thread: 128 when there is enough work to fill the chip, shorter otherwise.
 // OZL_MSM_WAVES=1 (experiment, measured and left off): pick the slice length that fills whole "waves" of resident
@@ -727,6 +727,9 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
       else if (use_tma && acc_mode == 3) k_accumulate_tma<F, 3><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 13 && F::N == 12) k_accumulate_tma<F, 3, (F::N == 12 ? 4 : 2)><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);   // experiment: 4 CTAs per SM at 128 registers
       else if (use_tma && acc_mode == 6 && F::N <= 12) k_accumulate_tma<F, (F::N <= 12 ? 6 : 0)><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);
+      else if (use_tma && acc_mode == 15 && F::N >= 16) {   // A/B: the other CTA count for the G2 curves (BN254 G2 ships 3, BLS12-381 G2 ships 2)
+        if constexpr (F::N >= 16) k_accumulate_tma<F, 5, (F::N == 16 ? 2 : 3)><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);
+      }
       else if (use_tma && acc_mode == 7) k_accumulate_tma<F, 7><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 5) k_accumulate_tma<F, 5><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);
       else if (use_tma && acc_mode == 4) k_accumulate_tma<F, 4><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
