@@ -1,8 +1,9 @@
 #!/bin/bash
 # A/B runs of the Groth16 prover's scheduling switches: "run NAME ENV=..." ; prints ms/proof, two-prover throughput, timeline
 run() {
+  EXTRA=${EXTRA:-}
   name=$1; shift
-  env "$@" python bench.py --workload groth16 --no-cpu-baseline > gpurun_out/g16_$name.json 2> gpurun_out/g16_$name.err
+  env "$@" python bench.py --workload groth16 --no-cpu-baseline $EXTRA > gpurun_out/g16_$name.json 2> gpurun_out/g16_$name.err
   python - "$name" "$TL" <<PY
 import json,sys
 n=sys.argv[1]
