@@ -800,7 +800,7 @@ def ntt_block(args, log_n: int = 24, device_index: int = 0, steps: int = 10):
         "e2e": {"value": n / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
                 "ms_per_step": e2e_s * 1e3, "api": "ozl_ntt (C ABI, pinned host buffer)"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_ntt_pass", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "roofline": {"kernel": "k_ntt_tile", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_transform": n * 64, "passes": passes, "avg_launch_ms": ms / max(passes, 1)},
         "fma_pipe": {"note": "binding roofline: one 254-bit Montgomery multiplication per butterfly",

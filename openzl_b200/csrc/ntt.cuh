@@ -142,7 +142,8 @@ k_ntt_pass(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ui
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared-memory tile pass: R = 3, 6 or 9 DIF stages per trip through HBM.
+// Shared-memory tile pass: R DIF stages per trip through HBM (R = 3, 6, 9 with radix-8 rounds; 4, 6, 8 with the
+// shipped radix-4 rounds, see NTT_TILE4_* below -- the description that follows is the radix-8 geometry).
 //
 // A CTA of 256 threads owns a tile of 2048 elements = M x C, M = 2^R points of one sub-transform (stride
 // q = n >> (s + R) apart in memory) times C = 2048 / M neighbouring sub-transforms ("columns": consecutive
@@ -166,21 +167,30 @@ static constexpr int NTT_TILE_THREADS = 256;
 // (ncu, unpadded: 5.9e7 bank conflicts in the last pass against 8.5e6 in the others)
 static constexpr int NTT_TILE_SMEM_HALVES = NTT_TILE_ELEMS + 512;
 static constexpr int NTT_TILE_SMEM_BYTES = 2 * NTT_TILE_SMEM_HALVES * 16;
+// radix-4 variant (shipped; OZL_NTT_R4=0 selects the radix-8 one): 1024-element tiles, four elements per thread, two
+// stages per round: 32 instead of 64 registers of data per thread, so four CTAs (32 warps) per SM instead of two (16)
+static constexpr int NTT_TILE4_ELEMS = 1024;
+static constexpr int NTT_TILE4_SMEM_HALVES = NTT_TILE4_ELEMS + 256;
+static constexpr int NTT_TILE4_SMEM_BYTES = 2 * NTT_TILE4_SMEM_HALVES * 16;
 
-// PAIRED: the four products of a stage go through two calls of the paired out-of-line multiplier (two independent
-// carry chains interleaved in one body) instead of four inlined bodies.
-template <class P, bool PAIRED = false>
-__global__ void __launch_bounds__(NTT_TILE_THREADS, 2)
+// G = stages per round (3: radix-8 groups, 2: radix-4 groups); a CTA of THREADS threads owns THREADS << G elements.
+// PAIRED: the products of a stage go through the paired out-of-line multiplier (two independent carry chains
+// interleaved in one body) instead of inlined bodies (measured slower: 128 registers, spills).
+template <class P, bool PAIRED = false, int G = 3, int THREADS = NTT_TILE_THREADS, int MINB = 2>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_ntt_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ tw, int log_n, int s, int R,
            int pre, int post, int last, const uint32_t* __restrict__ glo, const uint32_t* __restrict__ ghi,
            const Fp<P>* __restrict__ scale) {
   typedef Fp<P> F;
   static_assert(F::N == 8, "tile layout assumes 32-byte elements");
+  constexpr int NG = 1 << G, NH = NG / 2;
+  constexpr uint32_t TILE = (uint32_t)THREADS << G;
+  constexpr uint32_t HALVES = TILE + TILE / 4;
   extern __shared__ __align__(16) uint4 ntt_smem[];
   uint4* plane0 = ntt_smem;                            // low 16 bytes of every element
-  uint4* plane1 = ntt_smem + NTT_TILE_SMEM_HALVES;     // high 16 bytes
+  uint4* plane1 = ntt_smem + HALVES;                   // high 16 bytes
   const uint32_t n = 1u << log_n;
-  const uint32_t M = 1u << R, C = NTT_TILE_ELEMS >> R;
+  const uint32_t M = 1u << R, C = TILE >> R;
   const uint32_t q = n >> (s + R);                // memory stride between the points of one sub-transform
   const uint32_t u_base = blockIdx.x * C;         // first column: column u = blk * q + j0
   const int lo_bits = log_n < NTT_LO_BITS ? log_n : NTT_LO_BITS;
@@ -195,7 +205,7 @@ k_ntt_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ui
   const bool col_major = q == 1;                  // last pass: a column is contiguous in memory, columns are M apart
   const uint32_t RS = C + (col_major ? 1u : 0u);  // row stride of the tile in shared memory
   // ---- load -------------------------------------------------------------------------------
-  for (uint32_t t = tid; t < NTT_TILE_ELEMS; t += NTT_TILE_THREADS) {
+  for (uint32_t t = tid; t < TILE; t += THREADS) {
     const uint32_t m = col_major ? (t & (M - 1)) : (t / C);
     const uint32_t c = col_major ? (t >> R) : (t & (C - 1));
     const uint32_t i = col_base(c) + m * q;
@@ -208,76 +218,83 @@ k_ntt_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ui
     plane1[m * RS + c] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
   }
   __syncthreads();
-  // ---- rounds of three stages ---------------------------------------------------------------
+  // ---- rounds of G stages -------------------------------------------------------------------
   {
     const uint32_t c = tid & (C - 1);
     const uint32_t rest = tid / C;                // (blkl, jl) of this thread's group: one group per thread per round
     const uint32_t u = u_base + c;
     const uint32_t j0 = u - (u / q) * q;
 #pragma unroll 1
-    for (int ls = 0; ls < R; ls += 3) {
-      const uint32_t ql = M >> (ls + 3);
+    for (int ls = 0; ls < R; ls += G) {
+      const uint32_t ql = M >> (ls + G);
       const uint32_t blkl = rest / ql, jl = rest - blkl * ql;
       const uint32_t m0 = blkl * (M >> ls) + jl;
       // twiddle exponent of the butterfly at position i of stage r of this round (0 = unit twiddle).
       // Position i has been rotated left r times: the group index k it holds is i rotated right r times.
       auto exponent = [&](int r, int i) -> uint32_t {
-        const uint32_t k = ((uint32_t)i >> r) | (((uint32_t)i << (3 - r)) & 7u);
-        const uint32_t kmask = (4u >> r) - 1u;    // bits of k below the stage bit
+        const uint32_t k = ((uint32_t)i >> r) | (((uint32_t)i << (G - r)) & (uint32_t)(NG - 1));
+        const uint32_t kmask = ((uint32_t)NH >> r) - 1u;    // bits of k below the stage bit
         return ((jl + (k & kmask) * ql) * q + j0) << (s + ls + r);
       };
       // (Measured and rejected: prefetch.global.L1 of a stage's four twiddle lines one stage ahead -- 4.38 ms
       // against 4.27 ms at 2^24; the extra address arithmetic and LSU traffic cost more than the
       // long-scoreboard stalls they remove.)
-      F x[8];
+      F x[NG];
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
+      for (int k = 0; k < NG; k++) {
         const uint32_t a = (m0 + (uint32_t)k * ql) * RS + c;
         const uint4 l = plane0[a], h = plane1[a];
         x[k].v[0] = l.x; x[k].v[1] = l.y; x[k].v[2] = l.z; x[k].v[3] = l.w;
         x[k].v[4] = h.x; x[k].v[5] = h.y; x[k].v[6] = h.z; x[k].v[7] = h.w;
       }
 #pragma unroll 1
-      for (int r = 0; r < 3; r++) {
-        if (PAIRED) {
-          F w[4], d[4];
+      for (int r = 0; r < G; r++) {
+        if (PAIRED && G == 3) {
+          F w[NH], d[NH];
           bool any = false;
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
+          for (int i = 0; i < NH; i++) {
             const uint32_t e = exponent(r, i);
             w[i] = F::load(tw + (size_t)e * F::N);     // tw[0] = 1
             any |= e != 0;
-            const F a = x[i], b = x[i + 4];
+            const F a = x[i], b = x[i + NH];
             x[i] = a + b;
             d[i] = a - b;
           }
           if (any) {
-            const typename F::Pair p0 = F::mul2_ni(d[0], w[0], d[1], w[1]);
-            const typename F::Pair p1 = F::mul2_ni(d[2], w[2], d[3], w[3]);
-            x[4] = p0.a; x[5] = p0.b; x[6] = p1.a; x[7] = p1.b;
+#pragma unroll
+            for (int i = 0; i < NH; i += 2) {
+              const typename F::Pair p0 = F::mul2_ni(d[i], w[i], d[i + 1], w[i + 1]);
+              x[NH + i] = p0.a; x[NH + i + 1] = p0.b;
+            }
           } else {
-            x[4] = d[0]; x[5] = d[1]; x[6] = d[2]; x[7] = d[3];
+#pragma unroll
+            for (int i = 0; i < NH; i++) x[NH + i] = d[i];
           }
         } else {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const uint32_t e = exponent(r, i);
-          const F a = x[i], b = x[i + 4];
-          x[i] = a + b;
-          if (e == 0) {
-            x[i + 4] = a - b;
-          } else {
-            const F w = F::load(tw + (size_t)e * F::N);
-            x[i + 4] = (a - b) * w;
+          for (int i = 0; i < NH; i++) {
+            const uint32_t e = exponent(r, i);
+            const F a = x[i], b = x[i + NH];
+            x[i] = a + b;
+            if (e == 0) {
+              x[i + NH] = a - b;
+            } else {
+              const F w = F::load(tw + (size_t)e * F::N);
+              x[i + NH] = (a - b) * w;
+            }
           }
         }
-        }
-        // rotate the index bits left: b2 b1 b0 -> b1 b0 b2
-        const F t1 = x[1], t2 = x[2], t3 = x[3], t4 = x[4], t5 = x[5], t6 = x[6];
-        x[2] = t1; x[4] = t2; x[6] = t3; x[1] = t4; x[3] = t5; x[5] = t6;
+        // rotate the index bits left (b2 b1 b0 -> b1 b0 b2): the next stage's partners are NH apart again;
+        // G rotations are the identity, so a round leaves x[] in its original order
+        F y[NG];
+#pragma unroll
+        for (int i = 0; i < NG; i++) y[((i << 1) | (i >> (G - 1))) & (NG - 1)] = x[i];
+#pragma unroll
+        for (int i = 0; i < NG; i++) x[i] = y[i];
       }
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
+      for (int k = 0; k < NG; k++) {
         const uint32_t a = (m0 + (uint32_t)k * ql) * RS + c;
         plane0[a] = make_uint4(x[k].v[0], x[k].v[1], x[k].v[2], x[k].v[3]);
         plane1[a] = make_uint4(x[k].v[4], x[k].v[5], x[k].v[6], x[k].v[7]);
@@ -286,7 +303,7 @@ k_ntt_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ui
     }
   }
   // ---- store ------------------------------------------------------------------------------
-  for (uint32_t t = tid; t < NTT_TILE_ELEMS; t += NTT_TILE_THREADS) {
+  for (uint32_t t = tid; t < TILE; t += THREADS) {
     const uint32_t m = col_major ? (t & (M - 1)) : (t / C);
     const uint32_t c = col_major ? (t >> R) : (t & (C - 1));
     const uint32_t i = col_base(c) + m * q;
@@ -349,12 +366,28 @@ int ntt_run(cudaStream_t st, NttWorkspace& ws, int field_id, uint32_t* d_data, u
   const uint32_t* ghi = (const uint32_t*)ws.ghi[dir];
 
   // Pass plan.  Register-only passes of 1..3 stages (k_ntt_pass) for the remainder and for small domains;
-  // shared-memory tile passes of 3, 6 or 9 stages (k_ntt_tile) for the rest: 2^24 = 9 + 9 + 6 instead of
+  // shared-memory tile passes (k_ntt_tile) for the rest: 2^24 = 8 + 8 + 8 (radix-4 rounds) or 9 + 9 + 6 (radix-8) instead of
   // eight radix-8 trips through HBM.  OZL_NTT_TILE=0 selects the register-only plan for comparison.
   static const bool kTile = []() { const char* e = getenv("OZL_NTT_TILE"); return !(e && e[0] == '0'); }();
+  // OZL_NTT_R4: 0 = radix-8 rounds on 2048-element tiles (two CTAs per SM, 113 registers), 1 = radix-4 rounds on
+  // 1024-element tiles with three CTAs per SM (68 registers), 2 = the same with four (64 registers; DEFAULT).
+  // Measured at 2^24 BN254 Fr forward: 4.26 / 3.77 / 3.75 ms -- with half the data registers per thread twice the warps
+  // are resident (32 per SM) and the multiplier pipe stays fed through the load / store / barrier phases of a tile.
+  static const int kR4 = []() { const char* e = getenv("OZL_NTT_R4"); return e ? atoi(e) : 2; }();
   int radices[16], np = 0;
   bool tiled[16];
-  {
+  const bool r4 = kR4 > 0 && kTile && log_n >= 10;   // radix-4 rounds on 1024-element tiles: passes of 4, 6 or 8 stages
+  if (r4) {
+    const int rem = log_n % 2;
+    int L = log_n - rem;
+    if (rem) { tiled[np] = false; radices[np++] = 1; }
+    const int k = (L + 7) / 8;                // up to eight stages per pass: M <= 256 rows (padded rows fit), C >= 4 columns
+    for (int i = 0; i < k; i++) {
+      int R = ((L / 2 + (k - i) - 1) / (k - i)) * 2;
+      tiled[np] = true; radices[np++] = R;
+      L -= R;
+    }
+  } else {
     const int rem = log_n % 3;
     int L = log_n - rem;                       // multiple of 3
     const bool use_tiles = kTile && log_n >= 11;   // a tile holds 2048 elements
@@ -374,6 +407,8 @@ int ntt_run(cudaStream_t st, NttWorkspace& ws, int field_id, uint32_t* d_data, u
   static const bool kPaired = []() { const char* e = getenv("OZL_NTT_PAIRED"); return e && e[0] == '1'; }();
   if (cudaFuncSetAttribute(k_ntt_tile<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TILE_SMEM_BYTES) != cudaSuccess) return -3;
   if (cudaFuncSetAttribute(k_ntt_tile<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TILE_SMEM_BYTES) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_ntt_tile<P, false, 2, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TILE4_SMEM_BYTES) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_ntt_tile<P, false, 2, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TILE4_SMEM_BYTES) != cudaSuccess) return -3;
   uint32_t* scratch = (uint32_t*)ws.scratch;
   int s = 0;
   for (int pi = 0; pi < np; pi++) {
@@ -386,7 +421,9 @@ int ntt_run(cudaStream_t st, NttWorkspace& ws, int field_id, uint32_t* d_data, u
     if (lastp && inverse) post = coset ? 2 : 1;
     if (tiled[pi]) {
       const uint32_t blocks = (uint32_t)(n / NTT_TILE_ELEMS);
-      if (kPaired) k_ntt_tile<P, true><<<blocks, NTT_TILE_THREADS, NTT_TILE_SMEM_BYTES, st>>>(src, dst, tw, log_n, s, R, pre, post, lastp, glo, ghi, &consts->size_inv);
+      if (r4 && kR4 == 2) k_ntt_tile<P, false, 2, 256, 4><<<(uint32_t)(n / NTT_TILE4_ELEMS), 256, NTT_TILE4_SMEM_BYTES, st>>>(src, dst, tw, log_n, s, R, pre, post, lastp, glo, ghi, &consts->size_inv);
+      else if (r4) k_ntt_tile<P, false, 2, 256, 3><<<(uint32_t)(n / NTT_TILE4_ELEMS), 256, NTT_TILE4_SMEM_BYTES, st>>>(src, dst, tw, log_n, s, R, pre, post, lastp, glo, ghi, &consts->size_inv);
+      else if (kPaired) k_ntt_tile<P, true><<<blocks, NTT_TILE_THREADS, NTT_TILE_SMEM_BYTES, st>>>(src, dst, tw, log_n, s, R, pre, post, lastp, glo, ghi, &consts->size_inv);
       else k_ntt_tile<P, false><<<blocks, NTT_TILE_THREADS, NTT_TILE_SMEM_BYTES, st>>>(src, dst, tw, log_n, s, R, pre, post, lastp, glo, ghi, &consts->size_inv);
     } else {
       const uint32_t threads = (uint32_t)(n >> R);
