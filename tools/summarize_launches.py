@@ -29,6 +29,24 @@ if mode == "groth16":   # three consecutive k_spmv open a proof; take the 4th on
     pick = min(3, len(idx) - 1)
     start = idx[pick]
     end = idx[pick + 1] if pick + 1 < len(idx) else len(launches)
+if mode == "msm":   # one device-resident step: k_count .. next k_count, with one accumulation and one bucket reduction
+    bounds = [i for i, (n, _) in enumerate(launches) if n == "k_count"] + [len(launches)]
+    segs = [(a, b) for a, b in zip(bounds, bounds[1:])]
+    def ok(a, b):
+        names = [n for n, _ in launches[a:b]]
+        return names.count("k_accumulate_tma") == 1 and names.count("k_bucket_reduce") == 1 and "k_bench_mul" not in names
+    cands = [sg for sg in segs if ok(*sg)]
+    # the timed configuration is the one measured last; its device-resident steps have the longest accumulation
+    # (the batches of a host-scalar call accumulate a part of the points each)
+    def nsc(sg): return [n for n, _ in launches[sg[0]:sg[1]]].count("k_scatter_window")
+    def tacc(sg): return max(v for n, v in launches[sg[0]:sg[1]] if n == "k_accumulate_tma")
+    cands = [sg for sg in cands if nsc(sg) == nsc(cands[-1])]
+    start, end = max(cands, key=tacc)
+    # the step ends with k_final
+    for i in range(start, end):
+        if launches[i][0] == "k_final":
+            end = i + 1
+            break
 sel = launches[start:end]
 tot = sum(v for _, v in sel)
 agg, cnt = collections.OrderedDict(), collections.Counter()
