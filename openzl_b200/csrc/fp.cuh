@@ -340,6 +340,93 @@ struct Fp {
     return r;
   }
 
+  // ---- unreduced product and stand-alone reduction for lazily reduced Fq2 arithmetic -----------------
+  // t[0 .. 2N) = a * b (plain integers of N limbs, e.g. unreduced sums a0 + a1 < 2p), NO reduction.
+  // Two accumulators like the CIOS rows above so that every mad.lo / madc.hi pair lands on an even-aligned register
+  // pair and ptxas fuses it into one IMAD.WIDE: product a_j b_i goes to X[i + j] when i + j is even and to
+  // Y[i + j - 1] (Y limb k has weight 2^(32 (k + 1))) when it is odd; t = X + (Y << 32).
+  static OZL_DEV void mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* t) {
+    uint32_t X[2 * N], Y[2 * N];
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) { X[k] = 0; Y[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const int px = i & 1;                   // first j of the aligned chain
+#pragma unroll
+      for (int j = px; j < N; j += 2) {
+        const int sx = i + j;
+        X[sx] = (j == px) ? ptx::mad_lo_cc(a[j], b[i], X[sx]) : ptx::madc_lo_cc(a[j], b[i], X[sx]);
+        X[sx + 1] = ptx::madc_hi_cc(a[j], b[i], X[sx + 1]);
+      }
+      // the chain ends at limb i + px + N - 1; the limb above holds at most one carry bit so far (no product of an
+      // earlier row reaches it), and for the last row there is none: X <= a b < 2^(64 N)
+      if (i + px + N < 2 * N) X[i + px + N] = ptx::addc(X[i + px + N], 0);
+      const int py = 1 - px;                  // first j of the offset chain
+#pragma unroll
+      for (int j = py; j < N; j += 2) {
+        const int sy = i + j - 1;
+        Y[sy] = (j == py) ? ptx::mad_lo_cc(a[j], b[i], Y[sy]) : ptx::madc_lo_cc(a[j], b[i], Y[sy]);
+        Y[sy + 1] = ptx::madc_hi_cc(a[j], b[i], Y[sy + 1]);
+      }
+      if (i + N - px < 2 * N) Y[i + N - px] = ptx::addc(Y[i + N - px], 0);
+    }
+    t[0] = X[0];
+    t[1] = ptx::add_cc(X[1], Y[0]);
+#pragma unroll
+    for (int k = 2; k < 2 * N - 1; k++) t[k] = ptx::addc_cc(X[k], Y[k - 1]);
+    t[2 * N - 1] = ptx::addc(X[2 * N - 1], Y[2 * N - 2]);
+  }
+
+  // Divide the running value (X aligned with X[0] == 0, Y offset) by 2^32 and add `hi` at limb N - 1; on return the
+  // roles are swapped (Y aligned, X offset).  This is next_row() with the product row replaced by one injected limb.
+  static OZL_DEV void shift_inject(uint32_t* X, uint32_t* Y, uint32_t hi) {
+    Y[0] = ptx::add_cc(Y[0], X[1]);
+#pragma unroll
+    for (int k = 0; k < N - 2; k++) X[k] = ptx::addc_cc(X[k + 2], 0);
+    X[N - 2] = ptx::addc_cc(hi, 0);
+    X[N - 1] = ptx::addc(0, 0);
+  }
+
+  // Montgomery reduction of a 2N-limb value t < p 2^(32 N): t / 2^(32 N) mod p, fully reduced.  Same rows as the fused
+  // multiplication (N^2 aligned wide multiplies); the high limbs of t enter one per row.
+  static OZL_DEV Fp redc_cios(const uint32_t* t) {
+    static_assert(N % 2 == 0, "even limb count required");
+    uint32_t A[N], B[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) { A[k] = t[k]; B[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      reduce_row(A, B);
+      shift_inject(A, B, t[N + i]);
+      reduce_row(B, A);
+      shift_inject(B, A, t[N + i + 1]);
+    }
+    // A aligned, B offset; the value is < 2 p < 2^(32 N), so B[N - 1] == 0
+    Fp r;
+    r.v[0] = A[0];
+    r.v[1] = ptx::add_cc(A[1], B[0]);
+#pragma unroll
+    for (int k = 2; k < N - 1; k++) r.v[k] = ptx::addc_cc(A[k], B[k - 1]);
+    r.v[N - 1] = ptx::addc(A[N - 1], B[N - 2]);
+    final_sub(r.v);
+    return r;
+  }
+  // x += y, x -= y over M limbs (no reduction; the callers' bounds exclude carries / borrows out)
+  template <int M>
+  static OZL_DEV void add_limbs(uint32_t* x, const uint32_t* y) {
+    x[0] = ptx::add_cc(x[0], y[0]);
+#pragma unroll
+    for (int k = 1; k < M - 1; k++) x[k] = ptx::addc_cc(x[k], y[k]);
+    x[M - 1] = ptx::addc(x[M - 1], y[M - 1]);
+  }
+  template <int M>
+  static OZL_DEV void sub_limbs(uint32_t* x, const uint32_t* y) {
+    x[0] = ptx::sub_cc(x[0], y[0]);
+#pragma unroll
+    for (int k = 1; k < M - 1; k++) x[k] = ptx::subc_cc(x[k], y[k]);
+    x[M - 1] = ptx::subc(x[M - 1], y[M - 1]);
+  }
+
   // ---- Karatsuba product + separated Montgomery reduction -------------------------------------
   // t[0 .. 2H) = x * y for H-limb operands, schoolbook: row i adds x_j * y_i at limb i + j as two carry
   // chains (even j, odd j) over disjoint limb pairs, like the off-diagonal rows of sqr_sos().
@@ -578,6 +665,74 @@ struct Fp2 {
     r.c1 = t2 - t.a - t.b;
     return r;
   }
+  // Lazily reduced Karatsuba product: THREE unreduced base-field products and TWO Montgomery reductions, 5 N^2 wide
+  // multiplies instead of the 6 N^2 of three full multiplications:
+  //   t0 = a0 b0, t1 = a1 b1, t2 = (a0 + a1)(b0 + b1)  (sums unreduced: < 2p, so t2 < 4 p^2 < 2^(64 N))
+  //   c1 = redc(t2 - t0 - t1)  = a0 b1 + a1 b0 < 2 p^2 < p R
+  //   c0 = redc(t0 + p^2 - t1) in (0, 2 p^2)
+  // Needs 2 p < R / 2, true for both base fields (p < R / 4).
+  OZL_DEV Fp2 mul_lazy(const Fp2& o) const {
+    constexpr int BN = P::N;
+    static_assert(P::BITS <= 32 * BN - 2, "lazy reduction needs p < R / 4");
+    uint32_t sa[BN], sb[BN], t0[2 * BN], t1[2 * BN], t2[2 * BN];
+#pragma unroll
+    for (int k = 0; k < BN; k++) { sa[k] = c0.v[k]; sb[k] = o.c0.v[k]; }
+    Base::template add_limbs<BN>(sa, c1.v);
+    Base::template add_limbs<BN>(sb, o.c1.v);
+    Base::mul_wide(sa, sb, t2);
+    Base::mul_wide(c0.v, o.c0.v, t0);
+    Base::template sub_limbs<2 * BN>(t2, t0);
+    Base::mul_wide(c1.v, o.c1.v, t1);
+    Base::template sub_limbs<2 * BN>(t2, t1);
+    Fp2 r;
+    r.c1 = Base::redc_cios(t2);
+    Base::template add_limbs<2 * BN>(t0, P::modsq());
+    Base::template sub_limbs<2 * BN>(t0, t1);
+    r.c0 = Base::redc_cios(t0);
+    return r;
+  }
+  static OZL_DEV_NOINLINE Fp2 mul_lazy_ni(Fp2 a, Fp2 b) { return a.mul_lazy(b); }
+  // a b - c d with the same three-product shape for both terms and still TWO reductions (8 N^2 wide multiplies
+  // instead of 12 N^2): y3 = r (q - x3) - y p3 of every G2 addition.  The differences lie in (-2 p^2, 2 p^2); 2 p^2 is
+  // added before the reduction (4 p^2 < p R needs p < R / 4).
+  static OZL_DEV Fp2 mul_sub2_lazy(const Fp2& a, const Fp2& b, const Fp2& c, const Fp2& d) {
+    constexpr int BN = P::N;
+    static_assert(P::BITS <= 32 * BN - 2, "lazy reduction needs p < R / 4");
+    uint32_t sa[BN], sb[BN], w[2 * BN], dd[2 * BN], u[2 * BN];
+    // w = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1 ; dd = a0 b0 - a1 b1 + 2 p^2
+#pragma unroll
+    for (int k = 0; k < BN; k++) { sa[k] = a.c0.v[k]; sb[k] = b.c0.v[k]; }
+    Base::template add_limbs<BN>(sa, a.c1.v);
+    Base::template add_limbs<BN>(sb, b.c1.v);
+    Base::mul_wide(sa, sb, w);
+    Base::mul_wide(a.c0.v, b.c0.v, dd);
+    Base::template sub_limbs<2 * BN>(w, dd);
+    Base::mul_wide(a.c1.v, b.c1.v, u);
+    Base::template sub_limbs<2 * BN>(w, u);
+    Base::template add_limbs<2 * BN>(dd, P::modsq());
+    Base::template add_limbs<2 * BN>(dd, P::modsq());
+    Base::template sub_limbs<2 * BN>(dd, u);
+    // subtract the second product: w -= c0 d1 + c1 d0 (after adding 2 p^2) ; dd -= c0 d0 - c1 d1
+    Base::template add_limbs<2 * BN>(w, P::modsq());
+    Base::template add_limbs<2 * BN>(w, P::modsq());
+    Base::mul_wide(c.c0.v, d.c0.v, u);
+    Base::template sub_limbs<2 * BN>(dd, u);
+    Base::template add_limbs<2 * BN>(w, u);
+    Base::mul_wide(c.c1.v, d.c1.v, u);
+    Base::template add_limbs<2 * BN>(dd, u);
+    Base::template add_limbs<2 * BN>(w, u);
+#pragma unroll
+    for (int k = 0; k < BN; k++) { sa[k] = c.c0.v[k]; sb[k] = d.c0.v[k]; }
+    Base::template add_limbs<BN>(sa, c.c1.v);
+    Base::template add_limbs<BN>(sb, d.c1.v);
+    Base::mul_wide(sa, sb, u);
+    Base::template sub_limbs<2 * BN>(w, u);
+    Fp2 r;
+    r.c1 = Base::redc_cios(w);
+    r.c0 = Base::redc_cios(dd);
+    return r;
+  }
+  static OZL_DEV_NOINLINE Fp2 mul_sub2_lazy_ni(Fp2 a, Fp2 b, Fp2 c, Fp2 d) { return mul_sub2_lazy(a, b, c, d); }
   static OZL_DEV_NOINLINE Fp2 sqr_ni(Fp2 a) {
     typename Base::Pair t = Base::mul2_ni(a.c0 + a.c1, a.c0 - a.c1, a.c0, a.c1);
     Fp2 r;

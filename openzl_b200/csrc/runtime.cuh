@@ -526,7 +526,11 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
     const uint32_t groups = (uint32_t)p.Wc * parts;
     static const bool use_tma = []() { const char* e = getenv("OZL_ACC_TMA"); return !(e && e[0] == '0'); }();
     static const int acc_env = []() { const char* e = getenv("OZL_ACC_MODE"); return e ? atoi(e) : -1; }();
-    const int acc_mode = acc_env >= 0 ? acc_env : (F::N == 8 ? 6 : 5);   // BN254 G1 (8 limbs, ~45 KB inlined) is 4 % faster inlined + fused
+    // BN254 G1 (8 limbs, ~45 KB inlined) is 4 % faster inlined + fused; the G2 curves take the lazily reduced Fq2 products at
+    // two CTAs per SM (mode 18 for BN254 G2, 8 for BLS12-381 G2: accumulate 9.50 -> 9.26 ms and 23.25 -> 22.31 ms at 2^20 --
+    // 18 % fewer wide multiplies buy only 2-4 % because these kernels are bound by latency at 8 warps per SM, not by the pipe)
+    static const int acc_env_g2 = []() { const char* e = getenv("OZL_ACC_MODE_G2"); return e ? atoi(e) : -1; }();   // G2 curves only (A/B inside a Groth16 proof)
+    const int acc_mode = (F::N >= 16 && acc_env_g2 >= 0) ? acc_env_g2 : acc_env >= 0 ? acc_env : (F::N == 8 ? 6 : (F::N == 16 ? 18 : (F::N == 24 ? 8 : 5)));
     // intervals = accumulation launches of this batch: enough slices per launch for several full waves of the chip
     uint32_t intervals = 1;
     if (F::N <= 12 && !T && use_tma && acc_env < 0 && kPipe != 0 && groups > 1 && nj) {
@@ -729,6 +733,12 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
       else if (use_tma && acc_mode == 6 && F::N <= 12) k_accumulate_tma<F, (F::N <= 12 ? 6 : 0)><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);
       else if (use_tma && acc_mode == 15 && F::N >= 16) {   // A/B: the other CTA count for the G2 curves (BN254 G2 ships 3, BLS12-381 G2 ships 2)
         if constexpr (F::N >= 16) k_accumulate_tma<F, 5, (F::N == 16 ? 2 : 3)><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);
+      }
+      else if (use_tma && (acc_mode == 8 || acc_mode == 18) && F::N >= 16) {   // lazily reduced Fq2 products (G2 curves); 18 = with the other CTA count
+        if constexpr (F::N >= 16) {
+          if (acc_mode == 8) k_accumulate_tma<F, 8><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);
+          else k_accumulate_tma<F, 8, (F::N == 16 ? 2 : 3)><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);
+        }
       }
       else if (use_tma && acc_mode == 7) k_accumulate_tma<F, 7><<<ctx->sm_count * 4, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials);
       else if (use_tma && acc_mode == 5) k_accumulate_tma<F, 5><<<acc_grid, 128, 0, st>>>(b.d_pts, sorted, offsets, p.NB, acc_L, work_counter, partials, acc_batches);

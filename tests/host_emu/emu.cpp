@@ -31,9 +31,33 @@ static void fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
       if constexpr (F::Params::BITS <= 32 * F::Params::N - 2) r = F::mul_add2_ni(x, x, y, y);
       else r = x * x + y * y;
       break;
+    case 11:  // unreduced two-accumulator product followed by the stand-alone CIOS reduction (prime fields)
+      if constexpr (F::N == F::Params::N) {
+        uint32_t t[2 * F::N];
+        F::mul_wide(x.v, y.v, t);
+        r = F::redc_cios(t);
+      } else {
+        r = x.mul_lazy(y);                       // Fq2: lazily reduced Karatsuba (3 products, 2 reductions)
+      }
+      break;
+    case 12:  // Fq2: x y - y (x + y) with two reductions
+      if constexpr (F::N != F::Params::N) r = F::mul_sub2_lazy_ni(x, y, y, x + y);
+      else r = x * y - y * (x + y);
+      break;
     default: r = F::zero();
   }
   memcpy(out, &r, sizeof(F));
+}
+
+// raw limb-level entry points: a, b are ARBITRARY N-limb integers (not residues), t an arbitrary 2N-limb integer < p R
+template <class F>
+static void wide_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  if (op == 0) {
+    F::mul_wide(a, b, out);
+  } else {
+    F r = F::redc_cios(a);
+    memcpy(out, &r, sizeof(F));
+  }
 }
 
 template <class F>
@@ -81,6 +105,15 @@ void emu_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t
   }
 }
 // curve ids: 0 Bls12381G1, 1 Bls12381G2, 2 Bn254G1, 3 Bn254G2
+void emu_wide_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  switch (field) {
+    case 0: wide_op<Fp<Bls12381Fq>>(op, a, b, out); break;
+    case 1: wide_op<Fp<Bls12381Fr>>(op, a, b, out); break;
+    case 2: wide_op<Fp<Bn254Fq>>(op, a, b, out); break;
+    case 3: wide_op<Fp<Bn254Fr>>(op, a, b, out); break;
+  }
+}
+
 void emu_ec_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t k, uint32_t* out) {
   switch (curve) {
     case 0: ec_op<Fp<Bls12381Fq>>(op, a, b, k, out); break;

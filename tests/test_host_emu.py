@@ -93,6 +93,63 @@ def test_fp2_ops_match_oracle(emu, fid, f):
             assert dec(out) == exp, (op,)
 
 
+@pytest.mark.parametrize("fid,f", FIELD_IDS)
+def test_wide_product_and_cios_reduction(emu, fid, f):
+    """The building blocks of the lazily reduced Fq2 arithmetic: `Fp::mul_wide` (unreduced product of ARBITRARY
+    N-limb integers through two register-aligned accumulators) equals the integer product, `Fp::redc_cios`
+    (stand-alone Montgomery reduction, CIOS rows with the high limbs injected one per row) equals t / R mod p for
+    any t < p R, and their composition is the Montgomery product."""
+    n = f.limbs64 * 2
+    rnd = random.Random(100 + fid)
+    top = (1 << (32 * n)) - 1
+    R = 1 << (32 * n)
+    ints = [0, 1, top, top - 1, f.p, f.p - 1, 2 * f.p - 2, (1 << (32 * n - 1)), int("ffffffff00000000" * f.limbs64, 16),
+            int("00000000ffffffff" * f.limbs64, 16)] + [rnd.randrange(R) for _ in range(40)]
+    for a in ints:
+        for b in ints:
+            out = np.zeros(2 * n, dtype=np.uint32)
+            emu.emu_wide_op(fid, 0, P(l32(a, n)), P(l32(b, n)), P(out))
+            assert f32(out) == a * b, (f.name, hex(a), hex(b))
+    rinv = pow(R, -1, f.p)
+    ts = [0, 1, f.p * R - 1, f.p * R - f.p, f.p * f.p, 2 * f.p * f.p, R, R - 1, (f.p - 1) * (f.p - 1)] + [rnd.randrange(f.p * R) for _ in range(3000)]
+    ts = [t for t in ts if t < f.p * R]
+    for t in ts:
+        out = np.zeros(n, dtype=np.uint32)
+        emu.emu_wide_op(fid, 1, P(l32(t, 2 * n)), P(l32(0, n)), P(out))
+        assert f32(out) == t * rinv % f.p, (f.name, hex(t))
+    for a, b in [(a, b) for a in edge_values(f) for b in edge_values(f)] + [(rnd.randrange(f.p), rnd.randrange(f.p)) for _ in range(500)]:
+        out = np.zeros(n, dtype=np.uint32)
+        emu.emu_fp_op(fid, 11, P(l32(a, n)), P(l32(b, n)), P(out))
+        assert f32(out) == f.mont_mul(a, b)
+
+
+@pytest.mark.parametrize("fid,f", [(4, fields.BLS12_381_FQ), (5, fields.BN254_FQ)])
+def test_fp2_lazy_products_match_oracle(emu, fid, f):
+    """`Fp2::mul_lazy` (three unreduced products, two reductions) and `Fp2::mul_sub2_lazy` (a b - c d, six products, two
+    reductions) against the oracle's Fq2, on random operands and on every combination of extreme components."""
+    F2 = curves.Fp2Ops(f)
+    n = f.limbs64 * 2
+    rnd = random.Random(200 + fid)
+
+    def enc(a):
+        return np.concatenate([l32(f.to_mont(a[0]), n), l32(f.to_mont(a[1]), n)])
+
+    def dec(o):
+        return (f.from_mont(f32(o[:n])), f.from_mont(f32(o[n:])))
+
+    # components whose MONTGOMERY form is extreme (0, 1, p - 1, p - 2, R mod p) as well as random ones
+    ext = [f.from_mont(v) for v in (0, 1, f.p - 1, f.p - 2, f.R, (f.p - 1) // 2)]
+    cases = [((a0, a1), (b0, b1)) for a0 in ext for a1 in ext for b0 in ext[:4] for b1 in ext[:4]]
+    cases += [((rnd.randrange(f.p), rnd.randrange(f.p)), (rnd.randrange(f.p), rnd.randrange(f.p))) for _ in range(1500)]
+    for a, b in cases:
+        out = np.zeros(2 * n, dtype=np.uint32)
+        emu.emu_fp_op(fid, 11, P(enc(a)), P(enc(b)), P(out))
+        assert dec(out) == F2.mul(a, b), ("mul_lazy", a, b)
+        out = np.zeros(2 * n, dtype=np.uint32)
+        emu.emu_fp_op(fid, 12, P(enc(a)), P(enc(b)), P(out))
+        assert dec(out) == F2.sub(F2.mul(a, b), F2.mul(b, F2.add(a, b))), ("mul_sub2_lazy", a, b)
+
+
 CURVE_IDS = [(0, "bls12_381_g1"), (1, "bls12_381_g2"), (2, "bn254_g1"), (3, "bn254_g2")]
 
 
