@@ -284,6 +284,30 @@ def product_of_pairings_is_one(E: Engine, pairs: Sequence[Tuple[object, object]]
     return final_exponentiation(E, acc) == _f12_one()
 
 
+# ``PairingEngineExt`` of the plugin (/root/reference/plugins/arkworks/src/pairing.rs:46-90): same names, same meaning.
+# A "pair" is (G1 point, G2 point) in the affine tuples used throughout this module (None = identity).
+def eval(E: Engine, pair):   # noqa: A001  (the reference's name)
+    """``PairingEngineExt::eval``: the pairing function on one pair (pairing.rs:49-52)."""
+    return pairing(E, pair[0], pair[1])
+
+
+def has_same(E: Engine, lhs, rhs) -> bool:
+    """``PairingEngineExt::has_same``: both pairs evaluate to the same target-group element (pairing.rs:55-58)."""
+    return eval(E, lhs) == eval(E, rhs)
+
+
+def same(E: Engine, lhs, rhs):
+    """``PairingEngineExt::same``: ``Some((lhs, rhs))`` when the pairs evaluate to the same element, i.e. when there is
+    an r with r * lhs[0] == rhs[0] and lhs[1] == r * rhs[1]; ``None`` otherwise (pairing.rs:60-74)."""
+    return (lhs, rhs) if has_same(E, lhs, rhs) else None
+
+
+def same_ratio(E: Engine, lhs, rhs) -> bool:
+    """``PairingEngineExt::same_ratio``: the ratio of the G1 pair ``lhs = (L1, R1)`` equals the ratio of the G2 pair
+    ``rhs = (L2, R2)``: e(L1, R2) == e(R1, L2) (pairing.rs:76-88)."""
+    return has_same(E, (lhs[0], rhs[1]), (lhs[1], rhs[0]))
+
+
 # ---------------------------------------------------------------------------------------------
 # C-ABI layouts -> canonical integers
 # ---------------------------------------------------------------------------------------------

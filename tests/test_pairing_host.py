@@ -32,6 +32,25 @@ def test_bilinearity_and_non_degeneracy(name):
     assert not pr.product_of_pairings_is_one(E, [(aG, bH), (pr.g1_neg(E, pr.g1_mul(E, E.g1, a * b + 1)), E.g2)])
 
 
+@pytest.mark.parametrize("name", ["bn254", "bls12_381"])
+def test_valid_pairing_ratio_like_the_reference(name):
+    """The reference's own pairing test, restated (`assert_valid_pairing_ratio`, pairing.rs:104-129):
+    (g1, scalar * g2) and (scalar * g1, g2) evaluate to the same element -- through the mirrored
+    `PairingEngineExt::{same, has_same, same_ratio}` -- for random points of both groups."""
+    E = pr.ENGINES[name]
+    rnd = random.Random(7 + len(name))
+    for _ in range(2):
+        g1 = pr.g1_mul(E, E.g1, rnd.randrange(1, E.r))          # a random G1 / G2 element, like rng.gen()
+        g2 = pr.g2_mul(E, E.g2, rnd.randrange(1, E.r))
+        scalar = rnd.randrange(1, E.r)
+        lhs, rhs = (g1, pr.g2_mul(E, g2, scalar)), (pr.g1_mul(E, g1, scalar), g2)
+        assert pr.same(E, lhs, rhs) == (lhs, rhs)
+        assert pr.same(E, lhs, (pr.g1_mul(E, g1, scalar + 1), g2)) is None
+        # same_ratio((g1, s g1), (g2, s g2))
+        assert pr.same_ratio(E, (g1, pr.g1_mul(E, g1, scalar)), (g2, pr.g2_mul(E, g2, scalar)))
+        assert not pr.same_ratio(E, (g1, pr.g1_mul(E, g1, scalar)), (g2, pr.g2_mul(E, g2, scalar + 1)))
+
+
 def test_generators_match_the_oracle_curves():
     for name, E in pr.ENGINES.items():
         g1, g2 = curves.CURVES[name + "_g1"], curves.CURVES[name + "_g2"]
