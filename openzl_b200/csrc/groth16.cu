@@ -37,6 +37,9 @@ struct Groth16Pk {
   cudaStream_t s1 = nullptr, s2 = nullptr, s3 = nullptr;   // s3: the two variable-point scalar multiples of the assembly
   cudaEvent_t ev_z = nullptr, ev_s1 = nullptr, ev_s2 = nullptr, ev_ntt = nullptr, ev_a = nullptr, ev_b1 = nullptr, ev_s3 = nullptr, ev_fixed = nullptr;
   MsmWorkspace ws1, ws2;
+  // b_g1 and b_g2 queries have the same points at infinity (checked at creation): the b1 MSM reuses the b2 MSM's
+  // digit extraction and bucket sort (same scalars, same plan) instead of repeating them
+  bool share_b_sort = false;
 };
 
 }  // namespace ozl_rt
@@ -311,6 +314,18 @@ int ozl_groth16_pk_create(ozl_ctx* ctx, int pairing, uint32_t n_constraints, uin
     return rc;
   }
   pkp->h_a = a_query; pkp->h_b1 = b_g1_query; pkp->h_b2 = b_g2_query; pkp->h_h = h_query; pkp->h_l = l_query;
+  {
+    // same infinity sets?  (b_i(tau) = 0 kills the point in both groups; compared rather than assumed)
+    static const bool kShare = []() { const char* e = getenv("OZL_G16_SHARE_SORT"); return !(e && e[0] == '0'); }();
+    bool same = kShare && bb1->n == bb2->n && (bb1->d_inf == nullptr) == (bb2->d_inf == nullptr);
+    if (same && bb1->d_inf) {
+      const size_t bytes = (bb1->n + 7) / 8;
+      std::vector<uint8_t> m1(bytes), m2(bytes);
+      same = cudaMemcpy(m1.data(), bb1->d_inf, bytes, cudaMemcpyDeviceToHost) == cudaSuccess &&
+             cudaMemcpy(m2.data(), bb2->d_inf, bytes, cudaMemcpyDeviceToHost) == cudaSuccess && m1 == m2;
+    }
+    pkp->share_b_sort = same;
+  }
   ctx->pk_deleter = destroy_pk;
   *pk_handle = ctx->next_pk++;
   ctx->pks[*pk_handle] = pkp;
@@ -470,6 +485,7 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
     o1->scalar_mul_table(pk.s2, pk.tables_g1, fs, 4, fixed_out);
     o2->scalar_mul_table(pk.s2, pk.tables_g2, S + 8, 1, g2_fixed_out);
     CUDA_TRY(ctx, cudaEventRecord(pk.ev_fixed, pk.s2));
+    pk.ws2.publish_sort = pk.share_b_sort;
     if ((rc = ozl_rt_msm(ctx, pk.ws2, pk.s2, *q_b2, pk.zc, m, acc_g2))) return rc;
     if (early_ab) {   // B = beta2 + b2_acc + [s]delta2
       CUDA_TRY(ctx, cp_on(pk.s2, pts2 + 0 * J2, pk.consts_g2 + 0 * J2, J2));
@@ -499,7 +515,10 @@ int ozl_groth16_prove(ozl_ctx* ctx, uint32_t pk_handle, const uint64_t* z, const
         ctx->launches += 2;
       }
     }
-    if ((rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, *q_b1, pk.zc, m, acc + 3 * J1))) return rc;
+    pk.ws1.sort_from = pk.share_b_sort ? &pk.ws2 : nullptr;
+    rc = ozl_rt_msm(ctx, pk.ws1, pk.s1, *q_b1, pk.zc, m, acc + 3 * J1);
+    pk.ws1.sort_from = nullptr;
+    if (rc) return rc;
     if (kS3) {
       CUDA_TRY(ctx, cudaEventRecord(pk.ev_b1, pk.s1));
       CUDA_TRY(ctx, cudaStreamWaitEvent(pk.s3, pk.ev_b1, 0));

@@ -50,6 +50,20 @@ struct MsmWorkspace {
   // yield: accumulation launches of this workspace use a grid of short-lived CTAs (one 32-slice batch per warp)
   // instead of a persistent one, so that concurrent streams interleave by priority at every CTA boundary
   bool yield_ctas = false;
+  // Sort sharing.  Two MSMs over the SAME scalars whose bases have the same points at infinity and the same plan (the
+  // b_g1 and b_g2 queries of a Groth16 key) need one digit extraction and one bucket sort between them: the producer's
+  // workspace publishes its sort (publish_sort -> last_sort, ev_sorted), the consumer's names it in sort_from for the
+  // duration of one MSM and skips its own digits / scan / scatter stages when the descriptions match.
+  struct SortDesc {
+    const uint32_t* scalars = nullptr;
+    size_t n = 0, bases_n = 0;
+    int c = 0, W = 0, Wc = 0;
+    uint32_t L = 0;
+    bool valid = false;
+  } last_sort;
+  bool publish_sort = false;
+  cudaEvent_t ev_sorted = nullptr;
+  const MsmWorkspace* sort_from = nullptr;
   // pipelined MSM (msm_run_batched): two high-priority streams that take the accumulation launches of alternate bucket
   // intervals, one event per interval ("this interval is sorted") and one per stream ("its accumulations are through")
   cudaStream_t acc_stream[2] = {nullptr, nullptr};
@@ -477,12 +491,25 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
     uint32_t* offsets = (uint32_t*)ws.offsets[j].p;
     uint32_t* partials = (uint32_t*)ws.partials[j].p;
     const uint32_t* sc = d_scalars + first * 8;
+    bool reuse_sort = false;
+    if (ws.sort_from && J == 1 && !T && !mb.h_scalars) {
+      const MsmWorkspace::SortDesc& d = ws.sort_from->last_sort;
+      reuse_sort = d.valid && ws.sort_from->ev_sorted && d.scalars == d_scalars && d.n == n && d.bases_n == b.n && d.c == p.c &&
+                   d.W == p.W && d.Wc == p.Wc && d.L == Lj[0];
+    }
+    ws.last_sort.valid = false;
     if (mb.h_scalars) {
       if (nj) CUDA_TRY(ctx, cudaMemcpyAsync((void*)sc, mb.h_scalars + first * 4, nj * 32, cudaMemcpyHostToDevice, mb.copy_stream));
       CUDA_TRY(ctx, cudaEventRecord(mb.ev[j], mb.copy_stream));
       CUDA_TRY(ctx, cudaStreamWaitEvent(st, mb.ev[j], 0));
     }
 
+    if (reuse_sort) {
+      // the producer's offsets and sorted indices stand in for this MSM's own (its accumulation reads them only)
+      CUDA_TRY(ctx, cudaStreamWaitEvent(st, ws.sort_from->ev_sorted, 0));
+      offsets = (uint32_t*)ws.sort_from->offsets[0].p;
+      sorted = (uint32_t*)ws.sort_from->sorted.p;
+    } else {
     STAGE_ON(ctx, "digits_count", st);
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, (size_t)p.NB * 4, st));
     if (j) CUDA_TRY(ctx, cudaMemsetAsync(work_counter, 0, 4, st));
@@ -496,6 +523,7 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
     for (int l = 1; l <= T; l++)
       if ((r = run_scan(ctx, ws, st, counts, p.NB, lvl_off + (size_t)(l - 1) * (p.NB + 1), ScanCeilDiv{1u << l}))) return r;
     STAGE_END(ctx);
+    }   // !reuse_sort
 
     // ---- scatter + accumulate --------------------------------------------------------------------------------
     // The counting sort runs bucket-set-major, then one bucket RANGE of 2^18 buckets (8 MB of open 32-byte sectors)
@@ -533,7 +561,7 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
     const int acc_mode = (F::N >= 16 && acc_env_g2 >= 0) ? acc_env_g2 : acc_env >= 0 ? acc_env : (F::N == 8 ? 6 : (F::N == 16 ? 18 : (F::N == 24 ? 8 : 5)));
     // intervals = accumulation launches of this batch: enough slices per launch for several full waves of the chip
     uint32_t intervals = 1;
-    if (F::N <= 12 && !T && use_tma && acc_env < 0 && kPipe != 0 && groups > 1 && nj) {
+    if (F::N <= 12 && !T && use_tma && acc_env < 0 && kPipe != 0 && groups > 1 && nj && !reuse_sort) {
       const uint64_t slices = (uint64_t)nj * p.W / Lj[j];
       const uint64_t resident = (uint64_t)ctx->sm_count * AccPipe<F>::WARPS_PER_SM * 32;
       intervals = std::min<uint32_t>(groups, kPipe > 0 ? (uint32_t)kPipe : 8u);
@@ -611,7 +639,7 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
     STAGE_ON(ctx, "scatter", ss);
     {
       uint32_t k = 0, g_lo = 0;
-      for (uint32_t grp = 0; grp < groups && nj; grp++) {
+      for (uint32_t grp = 0; grp < groups && nj && !reuse_sort; grp++) {
         const uint32_t s_ = grp / parts, q = grp % parts;
         const uint32_t lo = q * span, hi = std::min<uint32_t>(p.B, lo + span);
         for (int w = (int)s_; w < p.W; w += p.Wc) {
@@ -659,6 +687,13 @@ int msm_run_batched(ozl_ctx* ctx, MsmWorkspace& ws, cudaStream_t st, const Bases
       }
     }
     if (!pipe) STAGE_END(ctx);
+    if (ws.publish_sort && J == 1 && !T && !pipe && !reuse_sort && !mb.h_scalars) {
+      if (!ws.ev_sorted) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ws.ev_sorted, cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventRecord(ws.ev_sorted, st));
+      ws.last_sort.scalars = d_scalars; ws.last_sort.n = n; ws.last_sort.bases_n = b.n;
+      ws.last_sort.c = p.c; ws.last_sort.W = p.W; ws.last_sort.Wc = p.Wc; ws.last_sort.L = Lj[0];
+      ws.last_sort.valid = true;
+    }
     // the next batch's digit extraction overwrites `digits` and `counts`: the main stream waits for the last scatter
     if (pipe) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ws.ev_interval[intervals - 1], 0));
 
@@ -924,6 +959,8 @@ inline void free_workspace(MsmWorkspace& ws) {
   for (auto& e : ws.ev_interval)
     if (e) { cudaEventDestroy(e); e = nullptr; }
   if (ws.sort_stream) { cudaStreamDestroy(ws.sort_stream); ws.sort_stream = nullptr; }
+  if (ws.ev_sorted) { cudaEventDestroy(ws.ev_sorted); ws.ev_sorted = nullptr; }
+  ws.last_sort.valid = false;
   if (ws.ev_sort_ready) { cudaEventDestroy(ws.ev_sort_ready); ws.ev_sort_ready = nullptr; }
 }
 
